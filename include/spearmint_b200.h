@@ -1,0 +1,144 @@
+/*
+ * spearmint_b200.h -- C ABI of the B200-native GP-EI hot path (libspearmint_b200.so).
+ *
+ * Drop-in boundary: the reference (JasperSnoek/spearmint) is pure Python and binds nothing
+ * native on this path, so the "FFI" a maintainer would add is a ctypes binding inside a
+ * chooser plugin.  Every entry point below replaces a span of the
+ * reference's numpy/scipy code; the span is cited as file:line relative to
+ * /root/reference/spearmint/spearmint  (GP = gp.py, OPT = chooser/GPEIOptChooser.py,
+ * PSEC = chooser/GPEIperSecChooser.py).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every function returns int: 0 ok; <0 bad argument (-(position)); >0 LAPACK-style info
+ *     (SMK_ERR_NOT_PD: a pivot was not positive, details in the info[] array);
+ *     SMK_ERR_CUDA (1000+cudaError) if a launch failed.
+ *   - device functions never allocate and never synchronise the stream; the caller passes
+ *     workspaces sized by the *_bytes() queries.  `stream` is a cudaStream_t cast to void*.
+ *   - T suffix _f32 / _f64: element type of every floating-point buffer of that call.
+ *   - matrices are row-major.  Npad = smk_npad(N) (N rounded up to a multiple of 128); factor
+ *     storage is [S][Npad][Npad] with the identity on the padding diagonal.
+ *   - `kind`: 0 SE (GP:87-93, ignores ls), 1 ARDSE (GP:95-100), 2 Matern32 (GP:107-113),
+ *     3 Matern52 (GP:120-127).
+ *   - per-sample hyper-parameters are device arrays: inv_ls[S][D] (=1/ls), amp2[S], noise[S],
+ *     mean[S]  -- one row per slice-sampled draw (the reference's hyper_samples list, OPT:628).
+ */
+#ifndef SPEARMINT_B200_H
+#define SPEARMINT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMK_OK 0
+#define SMK_ERR_NOT_PD 1
+#define SMK_ERR_CUDA 1000
+
+enum { SMK_SE = 0, SMK_ARDSE = 1, SMK_MATERN32 = 2, SMK_MATERN52 = 3 };
+
+/* ---- library info ------------------------------------------------------------------- */
+int smk_version(void);
+int smk_npad(int N);                       /* N rounded up to the factor block size (128)   */
+int smk_block(int elem_bytes);             /* diagonal-block size NB: 128 for f32, 64 for f64 */
+long long smk_launch_count(void);          /* kernels launched by this library so far        */
+const char* smk_last_error(void);          /* text of the last SMK_ERR_CUDA                  */
+
+/* ---- (1) covariance build: gp.dist2 + kernel + chooser.cov  (GP:34-54, GP:87-127, OPT:207-212)
+ * out[s][i][j] = amp2[s] * k_kind((X[i]-Y[j]) * inv_ls[s])  (+ diag below when Y == NULL)
+ * Y == NULL (self case): out is [S][ld][ld], ld >= N; diagonal gets amp2*1e-6 + diag_add[s]
+ *   (OPT:209-210 jitter plus the caller's noise*I, OPT:539), rows/cols N..ld-1 get the identity.
+ * Y != NULL (cross case): out is [S][N][ld], ld >= M, no diagonal term.
+ * diag_add may be NULL (treated as 0).                                                         */
+int smk_cov_build_f32(int kind, int N, int M, int D, int S, const float* X, const float* Y,
+                      const float* inv_ls, const float* amp2, const float* diag_add,
+                      float* out, int ld, void* stream);
+int smk_cov_build_f64(int kind, int N, int M, int D, int S, const double* X, const double* Y,
+                      const double* inv_ls, const double* amp2, const double* diag_add,
+                      double* out, int ld, void* stream);
+
+/* ---- (2) batched lower Cholesky: spla.cholesky(., lower=True)  (OPT:540, 567, 585)
+ * A: [S][Npad][Npad] in/out (lower triangle is read and overwritten with L; the strict upper
+ * triangle is left untouched).  winv: [S][Npad/NB][NB][NB] receives the inverses of the
+ * diagonal blocks of L (used by every triangular solve below).  info[s] = 0, or 1+index of
+ * the first non-positive pivot (the reference raises LinAlgError there).           */
+int smk_potrf_lower_batched_f32(int Npad, int S, float* A, float* winv, int* info, void* stream);
+int smk_potrf_lower_batched_f64(int Npad, int S, double* A, double* winv, int* info, void* stream);
+
+/* ---- (3) alpha = K^-1 (y - mean), log-determinant, quadratic form
+ *          spla.cho_solve((L,True), vals-mean)  (OPT:543, 603);  logprob pieces (OPT:637-640)
+ * y: [N] shared by all samples when y_stride == 0, else y + s*y_stride... with F right-hand sides
+ *    laid out y[f*ldy + n] (F columns, each contiguous), ldy >= N.
+ * alpha: [S][F][Npad] (padding zero).  sum_log_diag[s] = sum_i log L_ii;  quad[s][f] = r' K^-1 r.
+ * mean[s] is subtracted from every rhs (may be NULL).  alpha / sum_log_diag / quad may be NULL.  */
+int smk_chol_solve_f32(int N, int Npad, int S, int F, const float* L, const float* winv,
+                       const float* y, long long y_stride, int ldy, const float* mean,
+                       float* alpha, float* sum_log_diag, float* quad, void* stream);
+int smk_chol_solve_f64(int N, int Npad, int S, int F, const double* L, const double* winv,
+                       const double* y, long long y_stride, int ldy, const double* mean,
+                       double* alpha, double* sum_log_diag, double* quad, void* stream);
+
+/* ---- (4) fused predict: cross-covariance tiles generated on the fly -> blocked triangular
+ *          solve against L -> predictive mean and variance.  beta and Kx never reach HBM as
+ *          N x M matrices.            (OPT:535 cand_cross, OPT:544 beta, OPT:547-548 func_m/func_v)
+ * X: [N][D] observed (or observed+pending) inputs, C: [M][D] candidates.
+ * mu[s][j]  = C-cov(X, C_j)' alpha[s] + mean[s];   var[s][j] = amp2[s](1+1e-6) - |L^-1 Kx_j|^2
+ * mu, var: [S][ldm].  workspace: smk_predict_workspace_bytes(...) bytes.                        */
+size_t smk_predict_workspace_bytes(int elem_bytes, int Npad);
+int smk_predict_f32(int kind, int N, int Npad, int M, int D, int S, const float* X, const float* C,
+                    const float* inv_ls, const float* amp2, const float* mean, const float* L,
+                    const float* winv, const float* alpha, float* mu, float* var, int ldm,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int smk_predict_f64(int kind, int N, int Npad, int M, int D, int S, const double* X, const double* C,
+                    const double* inv_ls, const double* amp2, const double* mean, const double* L,
+                    const double* winv, const double* alpha, double* mu, double* var, int ldm,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (4b) cross mean only: mu[s][f][j] = cov(X, C_j)' alpha[s][f] + mean[s]
+ *          time-GP mean of EI-per-second (PSEC:442-459) and fantasy means (OPT:609).
+ * alpha: [S][F][Npad]; mu: [S][F][ldm].                                                         */
+int smk_cross_mean_f32(int kind, int N, int Npad, int M, int D, int S, int F, const float* X,
+                       const float* C, const float* inv_ls, const float* amp2, const float* mean,
+                       const float* alpha, float* mu, int ldm, void* stream);
+int smk_cross_mean_f64(int kind, int N, int Npad, int M, int D, int S, int F, const double* X,
+                       const double* C, const double* inv_ls, const double* amp2, const double* mean,
+                       const double* alpha, double* mu, int ldm, void* stream);
+
+/* ---- (5) EI sweep: the acquisition scan over candidates  (OPT:551-555; pending OPT:613-619;
+ *          per-second PSEC:490-491, 548)
+ * mu: [S][F][ldm], var: [S][ldm], best: [S][F] (the caller fills min(vals) or the per-fantasy
+ * bests, OPT:532 / OPT:597).  EI is evaluated in double, averaged over the F fantasies.
+ * log_time (optional, [S][ldm]): EI is divided by exp(log_time) (PSEC:459, 490).
+ * ei (optional): [S][ldm] per-sample EI;  ei_sum (optional): [ldm] += sum over s (caller zeroes). */
+int smk_ei_sweep_f32(int M, int S, int F, const float* mu, const float* var, int ldm,
+                     const float* best, const float* log_time, float* ei, float* ei_sum,
+                     void* stream);
+int smk_ei_sweep_f64(int M, int S, int F, const double* mu, const double* var, int ldm,
+                     const double* best, const double* log_time, double* ei, double* ei_sum,
+                     void* stream);
+
+/* ---- (6) selection: argsort(mean)[-k:] and argmax(mean)   (OPT:270-271, OPT:294)
+ * score: [M].  idx_out[k]: indices of the k largest scores in ASCENDING score order (so
+ * idx_out[k-1] is the argmax; ties resolved towards the lower index, numpy's first-max rule).
+ * workspace: smk_topk_workspace_bytes(M, k).                                                    */
+size_t smk_topk_workspace_bytes(int M, int k);
+int smk_topk_f32(int M, int k, const float* score, int* idx_out, float* val_out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int smk_topk_f64(int M, int k, const double* score, int* idx_out, double* val_out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (7) whole path with HOST buffers: GPEIOptChooser.ei_over_hypers, no pending (OPT:331-341)
+ * Copies inputs host->device, runs (1)-(5) for all S samples on the current device, copies the
+ * (S x M) EI matrix back (row s = sample s).  hypers as host arrays ls[S][D], amp2, noise, mean.
+ * Returns SMK_ERR_NOT_PD if any factorisation failed (info_out[S] optional).                      */
+int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const double* comp,
+                                const double* cand, const double* vals, const double* ls,
+                                const double* amp2, const double* noise, const double* mean,
+                                double* ei_out, int* info_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEARMINT_B200_H */

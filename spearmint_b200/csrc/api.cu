@@ -1,0 +1,222 @@
+// api.cu -- extern "C" surface of libspearmint_b200.so (see include/spearmint_b200.h).
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/spearmint_b200.h"
+#include "common.cuh"
+
+namespace smk {
+
+static std::atomic<long long> g_launches{0};
+static char g_err[512] = "";
+
+void count_launch(int n) { g_launches += n; }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return SMK_OK;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return SMK_ERR_CUDA + (int)e;
+}
+
+// implemented in the other translation units
+template <typename T>
+int cov_build(int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, T*, int, cudaStream_t);
+template <typename T>
+int potrf_lower_batched(int, int, T*, T*, int*, cudaStream_t);
+template <typename T>
+int chol_solve(int, int, int, int, const T*, const T*, const T*, long long, int, const T*, T*, T*, T*, cudaStream_t);
+template <typename T>
+int predict(int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, const T*,
+            const T*, T*, T*, int, void*, size_t, cudaStream_t);
+template <typename T>
+int cross_mean(int, int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, T*,
+               int, cudaStream_t);
+template <typename T>
+int ei_sweep(int, int, int, const T*, const T*, int, const T*, const T*, T*, T*, cudaStream_t);
+template <typename T>
+int topk(int, int, const T*, int*, T*, void*, size_t, cudaStream_t);
+size_t topk_workspace_bytes(int, int);
+size_t predict_workspace_bytes_any(int, int);
+
+}  // namespace smk
+
+using namespace smk;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int smk_version(void) { return 100; }
+int smk_npad(int N) { return ((N + kNpadMult - 1) / kNpadMult) * kNpadMult; }
+int smk_block(int elem_bytes) { return elem_bytes == 8 ? Cfg<double>::NB : Cfg<float>::NB; }
+long long smk_launch_count(void) { return g_launches.load(); }
+const char* smk_last_error(void) { return g_err; }
+
+int smk_cov_build_f32(int kind, int N, int M, int D, int S, const float* X, const float* Y, const float* inv_ls,
+                      const float* amp2, const float* diag_add, float* out, int ld, void* stream) {
+  return cov_build<float>(kind, N, M, D, S, X, Y, inv_ls, amp2, diag_add, out, ld, ST(stream));
+}
+int smk_cov_build_f64(int kind, int N, int M, int D, int S, const double* X, const double* Y, const double* inv_ls,
+                      const double* amp2, const double* diag_add, double* out, int ld, void* stream) {
+  return cov_build<double>(kind, N, M, D, S, X, Y, inv_ls, amp2, diag_add, out, ld, ST(stream));
+}
+
+int smk_potrf_lower_batched_f32(int Npad, int S, float* A, float* winv, int* info, void* stream) {
+  return potrf_lower_batched<float>(Npad, S, A, winv, info, ST(stream));
+}
+int smk_potrf_lower_batched_f64(int Npad, int S, double* A, double* winv, int* info, void* stream) {
+  return potrf_lower_batched<double>(Npad, S, A, winv, info, ST(stream));
+}
+
+int smk_chol_solve_f32(int N, int Npad, int S, int F, const float* L, const float* winv, const float* y,
+                       long long y_stride, int ldy, const float* mean, float* alpha, float* sum_log_diag,
+                       float* quad, void* stream) {
+  return chol_solve<float>(N, Npad, S, F, L, winv, y, y_stride, ldy, mean, alpha, sum_log_diag, quad, ST(stream));
+}
+int smk_chol_solve_f64(int N, int Npad, int S, int F, const double* L, const double* winv, const double* y,
+                       long long y_stride, int ldy, const double* mean, double* alpha, double* sum_log_diag,
+                       double* quad, void* stream) {
+  return chol_solve<double>(N, Npad, S, F, L, winv, y, y_stride, ldy, mean, alpha, sum_log_diag, quad, ST(stream));
+}
+
+size_t smk_predict_workspace_bytes(int elem_bytes, int Npad) { return predict_workspace_bytes_any(elem_bytes, Npad); }
+
+int smk_predict_f32(int kind, int N, int Npad, int M, int D, int S, const float* X, const float* C,
+                    const float* inv_ls, const float* amp2, const float* mean, const float* L, const float* winv,
+                    const float* alpha, float* mu, float* var, int ldm, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  return predict<float>(kind, N, Npad, M, D, S, X, C, inv_ls, amp2, mean, L, winv, alpha, mu, var, ldm, workspace,
+                        workspace_bytes, ST(stream));
+}
+int smk_predict_f64(int kind, int N, int Npad, int M, int D, int S, const double* X, const double* C,
+                    const double* inv_ls, const double* amp2, const double* mean, const double* L,
+                    const double* winv, const double* alpha, double* mu, double* var, int ldm, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return predict<double>(kind, N, Npad, M, D, S, X, C, inv_ls, amp2, mean, L, winv, alpha, mu, var, ldm, workspace,
+                         workspace_bytes, ST(stream));
+}
+
+int smk_cross_mean_f32(int kind, int N, int Npad, int M, int D, int S, int F, const float* X, const float* C,
+                       const float* inv_ls, const float* amp2, const float* mean, const float* alpha, float* mu,
+                       int ldm, void* stream) {
+  return cross_mean<float>(kind, N, Npad, M, D, S, F, X, C, inv_ls, amp2, mean, alpha, mu, ldm, ST(stream));
+}
+int smk_cross_mean_f64(int kind, int N, int Npad, int M, int D, int S, int F, const double* X, const double* C,
+                       const double* inv_ls, const double* amp2, const double* mean, const double* alpha,
+                       double* mu, int ldm, void* stream) {
+  return cross_mean<double>(kind, N, Npad, M, D, S, F, X, C, inv_ls, amp2, mean, alpha, mu, ldm, ST(stream));
+}
+
+int smk_ei_sweep_f32(int M, int S, int F, const float* mu, const float* var, int ldm, const float* best,
+                     const float* log_time, float* ei, float* ei_sum, void* stream) {
+  return ei_sweep<float>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ST(stream));
+}
+int smk_ei_sweep_f64(int M, int S, int F, const double* mu, const double* var, int ldm, const double* best,
+                     const double* log_time, double* ei, double* ei_sum, void* stream) {
+  return ei_sweep<double>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ST(stream));
+}
+
+size_t smk_topk_workspace_bytes(int M, int k) { return topk_workspace_bytes(M, k); }
+int smk_topk_f32(int M, int k, const float* score, int* idx_out, float* val_out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  return topk<float>(M, k, score, idx_out, val_out, workspace, workspace_bytes, ST(stream));
+}
+int smk_topk_f64(int M, int k, const double* score, int* idx_out, double* val_out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  return topk<double>(M, k, score, idx_out, val_out, workspace, workspace_bytes, ST(stream));
+}
+
+// -------------------------------------------------------------------------------------------------
+// Host-buffer pipeline: the call a non-Python host (or a ctypes stub) makes for ei_over_hypers.
+// Device buffers are cached between calls (grow-only) so steady-state calls do no cudaMalloc.
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = 0;
+      if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+      cap = bytes;
+    }
+    return p;
+  }
+};
+DevBuf g_in, g_fac, g_winv, g_alpha, g_mv, g_ws, g_ei;
+std::vector<float> g_host;
+}  // namespace
+
+int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const double* comp, const double* cand,
+                                const double* vals, const double* ls, const double* amp2, const double* noise,
+                                const double* mean, double* ei_out, int* info_out) {
+  if (kind < 0 || kind > 3) return -1;
+  if (N <= 0) return -2;
+  if (M <= 0) return -3;
+  if (D <= 0) return -4;
+  if (S <= 0) return -5;
+  if (!comp || !cand || !vals || !ls || !amp2 || !noise || !mean || !ei_out) return -6;
+  const int Npad = smk_npad(N), NB = Cfg<float>::NB, ldm = ((M + 127) / 128) * 128;
+  cudaStream_t st = 0;
+  // ---- pack all small inputs into one pinned-size host block: X | C | y | inv_ls | amp2 | noise | mean | best
+  const size_t nX = (size_t)N * D, nC = (size_t)M * D, nH = (size_t)S * D;
+  const size_t tot = nX + nC + N + nH + 4 * (size_t)S;
+  g_host.resize(tot);
+  float* h = g_host.data();
+  float *hX = h, *hC = hX + nX, *hy = hC + nC, *hil = hy + N, *ha = hil + nH, *hn = ha + S, *hm = hn + S,
+        *hb = hm + S;
+  for (size_t i = 0; i < nX; ++i) hX[i] = (float)comp[i];
+  for (size_t i = 0; i < nC; ++i) hC[i] = (float)cand[i];
+  double best = vals[0];
+  for (int i = 0; i < N; ++i) { hy[i] = (float)vals[i]; if (vals[i] < best) best = vals[i]; }
+  for (size_t i = 0; i < nH; ++i) hil[i] = (kind == SMK_SE) ? 1.0f : (float)(1.0 / ls[i]);
+  for (int s = 0; s < S; ++s) { ha[s] = (float)amp2[s]; hn[s] = (float)noise[s]; hm[s] = (float)mean[s]; hb[s] = (float)best; }
+
+  float* d = (float*)g_in.get(tot * sizeof(float));
+  float* fac = (float*)g_fac.get((size_t)S * Npad * Npad * sizeof(float));
+  float* winv = (float*)g_winv.get((size_t)S * Npad * NB * sizeof(float));
+  float* alpha = (float*)g_alpha.get((size_t)S * Npad * sizeof(float));
+  float* mv = (float*)g_mv.get(2 * (size_t)S * ldm * sizeof(float));
+  float* ei = (float*)g_ei.get((size_t)S * ldm * sizeof(float) + S * sizeof(int));
+  const size_t wsb = smk_predict_workspace_bytes(4, Npad);
+  void* ws = g_ws.get(wsb);
+  if (!d || !fac || !winv || !alpha || !mv || !ei || !ws) {
+    snprintf(g_err, sizeof(g_err), "cudaMalloc failed");
+    return SMK_ERR_CUDA;
+  }
+  int* info = reinterpret_cast<int*>(ei + (size_t)S * ldm);
+  cudaMemcpyAsync(d, h, tot * sizeof(float), cudaMemcpyHostToDevice, st);
+  float *dX = d, *dC = dX + nX, *dy = dC + nC, *dil = dy + N, *da = dil + nH, *dn = da + S, *dm = dn + S,
+        *db = dm + S;
+  int rc;
+  if ((rc = smk_cov_build_f32(kind, N, N, D, S, dX, nullptr, dil, da, dn, fac, Npad, st))) return rc;
+  if ((rc = smk_potrf_lower_batched_f32(Npad, S, fac, winv, info, st))) return rc;
+  if ((rc = smk_chol_solve_f32(N, Npad, S, 1, fac, winv, dy, 0, N, dm, alpha, nullptr, nullptr, st))) return rc;
+  if ((rc = smk_predict_f32(kind, N, Npad, M, D, S, dX, dC, dil, da, dm, fac, winv, alpha, mv, mv + (size_t)S * ldm,
+                            ldm, ws, wsb, st)))
+    return rc;
+  if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, st))) return rc;
+  std::vector<float> hout((size_t)S * ldm);
+  std::vector<int> hinfo(S);
+  cudaMemcpyAsync(hout.data(), ei, hout.size() * sizeof(float), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hinfo.data(), info, S * sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "ei_over_hypers_host: %s", cudaGetErrorString(e));
+    return SMK_ERR_CUDA + (int)e;
+  }
+  int bad = 0;
+  for (int s = 0; s < S; ++s) {
+    if (info_out) info_out[s] = hinfo[s];
+    if (hinfo[s]) bad = 1;
+    for (int j = 0; j < M; ++j) ei_out[(size_t)s * M + j] = (double)hout[(size_t)s * ldm + j];
+  }
+  return bad ? SMK_ERR_NOT_PD : SMK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""-m gpu: the whole EI path (engine / C-ABI) against golden vectors frozen from the REAL reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py through oracle/ref_shim.py).
+
+Stated fp64 -> fp32 tolerance:
+    per candidate |EI_gpu - EI_ref| <= 5e-3 * max_j EI_ref[j]   (per hyper-sample column)
+    argmax of the mean over samples identical whenever the reference's top-2 gap exceeds that tolerance.
+The float64 build of the same kernels must agree to 1e-7 relative (logic check, no precision slack).
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import OPT_CASES, PSEC_CASES, hypers, load, sets
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines():
+    import torch
+    from spearmint_b200.engine import GPEIEngine
+    return {"f32": GPEIEngine(dtype=torch.float32), "f64": GPEIEngine(dtype=torch.float64)}
+
+
+def _check(ei, ref, prec):
+    assert ei.shape == ref.shape
+    assert np.all(np.isfinite(ei))
+    for s in range(ref.shape[1]):
+        scale = np.abs(ref[:, s]).max()
+        tol = (5e-3 if prec == "f32" else 1e-7) * scale
+        assert np.abs(ei[:, s] - ref[:, s]).max() <= tol, (s, np.abs(ei[:, s] - ref[:, s]).max(), scale)
+    mref, mgot = ref.mean(axis=1), ei.mean(axis=1)
+    top2 = np.sort(mref)[-2:]
+    gap = top2[1] - top2[0]
+    if gap > 2 * (5e-3 if prec == "f32" else 1e-7) * np.abs(mref).max():
+        assert int(np.argmax(mgot)) == int(np.argmax(mref))
+
+
+@pytest.mark.parametrize("name", OPT_CASES)
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_ei_over_hypers_vs_reference(engines, name, prec):
+    g = load(name)
+    comp, pend, cand, vals = sets(g)
+    ei = engines[prec].ei_over_hypers(str(g["kind"]), hypers(g), comp, pend, cand, vals, g["normals"])
+    _check(ei, g["overall_ei"], prec)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_ei_per_second_vs_reference(engines, prec):
+    g = load("psec_d4")
+    comp, pend, cand, vals = sets(g)
+    durs = np.log(g["durations"][g["complete"]])
+    hs, ths = hypers(g), hypers(g, "ths")
+    S = int(g["S"])
+    ei = engines[prec].ei_over_hypers(str(g["kind"]), hs, comp, pend, cand, vals, None, ths[:S], durs)
+    _check(ei, g["per_sample_ei_per_s"], prec)
+
+
+def test_c_abi_host_entry_point():
+    """smk_ei_over_hypers_host_f32: plain host pointers in, EI matrix out (the non-Python binding)."""
+    import ctypes as C
+    from spearmint_b200 import _lib
+    g = load("opt_d8_m52")
+    comp, pend, cand, vals = sets(g)
+    hs = hypers(g)
+    S, (N, D), M = len(hs), comp.shape, cand.shape[0]
+    ls = np.ascontiguousarray(np.vstack([h[3] for h in hs]))
+    amp2 = np.array([h[2] for h in hs])
+    noise = np.array([h[1] for h in hs])
+    mean = np.array([h[0] for h in hs])
+    out = np.zeros((S, M))
+    info = np.zeros(S, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    compc, candc, valsc = (np.ascontiguousarray(a, dtype=np.float64) for a in (comp, cand, vals))
+    rc = _lib.lib().smk_ei_over_hypers_host_f32(3, N, M, D, S, p(compc), p(candc), p(valsc), p(ls), p(amp2),
+                                                p(noise), p(mean), p(out), p(info))
+    assert rc == 0 and np.all(info == 0)
+    _check(out.T, g["overall_ei"], "f32")
+    assert _lib.lib().smk_launch_count() > 0

@@ -1,0 +1,188 @@
+"""-m gpu: every C-ABI entry point against the CPU oracle on seeded inputs (float64 build bit-tight,
+float32 build within the stated fp64->fp32 tolerances)."""
+import numpy as np
+import pytest
+import scipy.linalg as spla
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["SE", "ARDSE", "Matern32", "Matern52"]
+
+
+@pytest.fixture(scope="module")
+def engines():
+    import torch
+    from spearmint_b200.engine import GPEIEngine
+    return {"f32": GPEIEngine(dtype=torch.float32), "f64": GPEIEngine(dtype=torch.float64)}
+
+
+def _problem(D, N, M, S, seed, noise=1e-3):
+    rs = np.random.RandomState(seed)
+    X, Cd = rs.rand(N, D), rs.rand(M, D)
+    y = np.sin(3 * X).sum(1) + 0.01 * rs.randn(N)
+    y = (y - y.mean()) / y.std()
+    hs = [(0.1 * rs.randn(), noise, float(np.exp(0.25 * rs.randn())), rs.uniform(0.3, 2.0, D)) for _ in range(S)]
+    return X, Cd, y, hs
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_cov_build(engines, kind, prec):
+    eng = engines[prec]
+    X, Cd, y, hs = _problem(5, 70, 45, 3, 1)
+    hb = eng.hypers(hs, kind)
+    Ks = eng.cov(kind, hb, eng.to_dev(X)).double().cpu().numpy()
+    Kc = eng.cov(kind, hb, eng.to_dev(X), eng.to_dev(Cd)).double().cpu().numpy()
+    tol = dict(rtol=1e-12, atol=1e-13) if prec == "f64" else dict(rtol=2e-5, atol=2e-6)
+    for s, h in enumerate(hs):
+        np.testing.assert_allclose(Ks[s], O.cov(kind, h[2], h[3], X), **tol)
+        np.testing.assert_allclose(Kc[s], O.cov(kind, h[2], h[3], X, Cd), **tol)
+
+
+@pytest.mark.parametrize("prec,N", [("f64", 64), ("f64", 200), ("f32", 128), ("f32", 300), ("f32", 700)])
+def test_potrf_and_solve(engines, prec, N):
+    import torch
+    eng = engines[prec]
+    X, Cd, y, hs = _problem(6, N, 10, 3, 2)
+    hb = eng.hypers(hs, "Matern52")
+    fac = eng.factor("Matern52", eng.to_dev(X), hb)
+    fac.check_pd()
+    L = fac.L.double().cpu().numpy()
+    tol = 1e-11 if prec == "f64" else 3e-4
+    yd = eng.to_dev(y)
+    alpha, sld, quad = fac.solve(yd, F=1, want_logdet=True, want_quad=True)
+    alpha = alpha.double().cpu().numpy()
+    NB = eng.NB
+    for s, h in enumerate(hs):
+        K = O.cov("Matern52", h[2], h[3], X) + h[1] * np.eye(N)
+        Lref = spla.cholesky(K, lower=True)
+        Lg = np.tril(L[s, :N, :N])
+        assert np.abs(Lg - Lref).max() <= tol * np.abs(Lref).max()
+        # padding carries the identity
+        pad = L[s, N:, N:]
+        assert np.allclose(np.tril(pad), np.eye(pad.shape[0]))
+        # diagonal-block inverses
+        W = fac.winv[s].double().cpu().numpy()
+        for b in range(min(2, fac.Npad // NB)):
+            blk = np.tril(L[s, b * NB:(b + 1) * NB, b * NB:(b + 1) * NB])
+            assert np.abs(W[b].dot(blk) - np.eye(NB)).max() < (1e-10 if prec == "f64" else 2e-3)
+        a_ref = spla.cho_solve((Lref, True), y - h[0])
+        assert np.abs(alpha[s, 0, :N] - a_ref).max() <= (1e-8 if prec == "f64" else 2e-2) * np.abs(a_ref).max()
+        assert np.all(alpha[s, 0, N:] == 0)
+        np.testing.assert_allclose(float(sld[s]), np.sum(np.log(np.diag(Lref))), rtol=1e-10 if prec == "f64" else 2e-5)
+        np.testing.assert_allclose(float(quad[s, 0]), (y - h[0]).dot(a_ref), rtol=1e-9 if prec == "f64" else 5e-3)
+
+
+def test_potrf_reports_not_pd(engines):
+    import torch
+    eng = engines["f32"]
+    X = np.random.RandomState(0).rand(40, 3)
+    hb = eng.hypers([(0.0, -5.0, 1.0, np.ones(3))], "Matern52")   # negative "noise" -> indefinite
+    fac = eng.factor("Matern52", eng.to_dev(X), hb)
+    with pytest.raises(np.linalg.LinAlgError):
+        fac.check_pd()
+
+
+def test_solve_multiple_rhs_and_leading_block(engines):
+    eng = engines["f64"]
+    N, P, F = 90, 5, 7
+    X, Cd, y, hs = _problem(4, N + P, 10, 2, 3)
+    hb = eng.hypers(hs, "Matern52")
+    fac = eng.factor("Matern52", eng.to_dev(X), hb)
+    rs = np.random.RandomState(5)
+    Y = rs.randn(2, F, N + P)
+    a, _, q = fac.solve(eng.to_dev(Y), F=F, y_stride=F * (N + P), ldy=N + P, want_quad=True)
+    a = a.cpu().numpy()
+    al, _, _ = fac.solve(eng.to_dev(y[:N]), F=1, n_lead=N)
+    al = al.cpu().numpy()
+    for s, h in enumerate(hs):
+        K = O.cov("Matern52", h[2], h[3], X) + h[1] * np.eye(N + P)
+        ref = np.linalg.solve(K, (Y[s] - h[0]).T).T
+        np.testing.assert_allclose(a[s, :, :N + P], ref, rtol=1e-8, atol=1e-9)
+        ref_l = np.linalg.solve(K[:N, :N], y[:N] - h[0])
+        np.testing.assert_allclose(al[s, 0, :N], ref_l, rtol=1e-8, atol=1e-9)
+        assert np.all(al[s, 0, N:] == 0)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("prec,D,N,M", [("f64", 3, 50, 97), ("f64", 40, 130, 300), ("f32", 8, 200, 1000),
+                                        ("f32", 1, 33, 130), ("f32", 33, 260, 515)])
+def test_predict_moments(engines, kind, prec, D, N, M):
+    eng = engines[prec]
+    X, Cd, y, hs = _problem(D, N, M, 3, 4)
+    hb = eng.hypers(hs, kind)
+    fac = eng.factor(kind, eng.to_dev(X), hb)
+    fac.check_pd()
+    alpha, _, _ = fac.solve(eng.to_dev(y), F=1)
+    mu, var, ldm = eng.predict(kind, fac, eng.to_dev(Cd), alpha)
+    mu, var = mu.double().cpu().numpy()[:, :M], var.double().cpu().numpy()[:, :M]
+    for s, h in enumerate(hs):
+        m_ref, v_ref, _, _ = O.predict(kind, h, X, Cd, y)
+        if prec == "f64":
+            np.testing.assert_allclose(mu[s], m_ref, rtol=1e-8, atol=1e-9)
+            np.testing.assert_allclose(var[s], v_ref, rtol=1e-7, atol=1e-9)
+        else:
+            np.testing.assert_allclose(mu[s], m_ref, rtol=1e-4, atol=2e-4)       # mean rtol 1e-4
+            np.testing.assert_allclose(var[s], v_ref, rtol=1e-3, atol=2e-4 * h[2])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_cross_mean(engines, prec):
+    eng = engines[prec]
+    D, N, M, F = 5, 77, 210, 11
+    X, Cd, y, hs = _problem(D, N, M, 2, 6)
+    hb = eng.hypers(hs, "Matern52")
+    fac = eng.factor("Matern52", eng.to_dev(X), hb)
+    rs = np.random.RandomState(7)
+    A = rs.randn(2, F, fac.Npad)
+    A[:, :, N:] = 0
+    mu = eng.cross_mean("Matern52", fac, eng.to_dev(Cd), eng.to_dev(A), F).double().cpu().numpy()
+    for s, h in enumerate(hs):
+        Kx = O.cov("Matern52", h[2], h[3], X, Cd)
+        ref = A[s, :, :N].dot(Kx) + h[0]
+        np.testing.assert_allclose(mu[s, :, :M], ref, rtol=1e-9 if prec == "f64" else 2e-4,
+                                   atol=1e-10 if prec == "f64" else 2e-4)
+
+
+@pytest.mark.parametrize("F", [1, 6])
+def test_ei_sweep(engines, F):
+    import torch
+    eng = engines["f32"]
+    rs = np.random.RandomState(8)
+    S, M = 5, 1000
+    ldm = 1024
+    mu = rs.randn(S, F, ldm).astype(np.float32)
+    var = np.abs(rs.randn(S, ldm)).astype(np.float32) * 0.5 + 1e-4
+    var[0, :10] *= 1e-4            # deep tail: u << 0
+    mu[0, :, :10] += 3.0
+    best = rs.randn(S, F).astype(np.float32) - 1.0
+    lt = (0.3 * rs.randn(S, ldm)).astype(np.float32)
+    for log_time in (None, lt):
+        ei, ei_sum = eng.ei_sweep(M, S, F, torch.from_numpy(mu).cuda(), torch.from_numpy(var).cuda(), ldm,
+                                  torch.from_numpy(best).cuda(),
+                                  None if log_time is None else torch.from_numpy(log_time).cuda())
+        ref = np.zeros((S, M))
+        for s in range(S):
+            sdev = np.sqrt(var[s, :M].astype(float))[:, None]
+            e = O._ei_from_moments(best[s].astype(float)[None, :], mu[s, :, :M].astype(float).T, sdev).mean(axis=1)
+            ref[s] = e / (np.exp(log_time[s, :M].astype(float)) if log_time is not None else 1.0)
+        got = ei.double().cpu().numpy()[:, :M]
+        np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-30)          # fp32 storage of a double evaluation
+        np.testing.assert_allclose(ei_sum.double().cpu().numpy()[:M], ref.sum(0), rtol=5e-6, atol=1e-30)
+
+
+@pytest.mark.parametrize("M,k", [(10, 3), (5000, 20), (100000, 20), (4097, 1)])
+def test_topk_matches_numpy(engines, M, k):
+    import torch
+    eng = engines["f32"]
+    rs = np.random.RandomState(9)
+    score = rs.rand(M).astype(np.float32)
+    score[rs.randint(0, M, size=max(1, M // 50))] = score.max()   # ties at the top -> first-max rule
+    idx, val = eng.topk(torch.from_numpy(score).cuda(), M, k)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    assert idx[-1] == int(np.argmax(score))
+    order = np.lexsort((-np.arange(M), score))       # ascending score, ties: higher index first
+    np.testing.assert_array_equal(idx, order[-k:])
+    np.testing.assert_array_equal(val, score[idx])
