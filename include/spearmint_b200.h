@@ -138,6 +138,21 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
                                 const double* amp2, const double* noise, const double* mean,
                                 double* ei_out, int* info_out);
 
+/* ---- (8) EI value + input-gradient terms at Q query points with cached factors
+ *          GPEIOptChooser.grad_optimize_ei (OPT:391-525), gp.grad_dist2 / grad_<kernel> (GP:56-85, 102-132)
+ * alpha: [S][F][Npad] (K^-1 (y_f - mean));  gamma: [S][Q][Npad] (K^-1 kx_q, from smk_chol_solve with the
+ * cross-covariance columns as right-hand sides);  xq: [Q][D] query points.
+ * out: [S][Q][F+1][D+1]:  out[f][d] = sum_n alpha_f[n] gk[n][d];  out[f][D] = kx' alpha_f;
+ *                         out[F][d] = sum_n gamma[n] gk[n][d];     out[F][D] = kx' K^-1 kx,
+ * with gk[n][d] = dk/dr2 * (2/ls_d) (X[n][d] - xq[d]) / ls_d  (correlation gradient, no amp2 -- the
+ * reference applies 0.5*amp2 afterwards, OPT:437).  kind SMK_SE is rejected like the reference (no gp.grad_SE). */
+int smk_ei_grad_terms_f32(int kind, int N, int Npad, int D, int S, int Q, int F, const float* X, const float* xq,
+                          const float* inv_ls, const float* amp2, const float* alpha, const float* gamma,
+                          float* out, void* stream);
+int smk_ei_grad_terms_f64(int kind, int N, int Npad, int D, int S, int Q, int F, const double* X, const double* xq,
+                          const double* inv_ls, const double* amp2, const double* alpha, const double* gamma,
+                          double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

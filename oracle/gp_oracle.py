@@ -268,3 +268,47 @@ def grad_optimize_ei_over_hypers(kind, hyper_samples, cand, comp, pend, vals, no
         fi, gi = grad_optimize_ei(kind, h, cand, comp, pend, vals, normals)
         f, g = f + fi, g + gi
     return f, g
+
+
+# ----------------------------------------------------------------------------- EI per second: value + gradient
+def grad_optimize_ei_per_s(kind, hyper, time_hyper, cand, comp, vals, durs_log):
+    """(f, g) of GPEIperSecChooser.grad_optimize_ei for one point / one sample pair (PSEC:351-435).
+
+    Pending points are ignored by the reference on this path; the 0.5*amp2 prefactors (PSEC:431-432) are kept."""
+    mean, noise, amp2, ls = hyper
+    tmean, tnoise, tamp2, tls = time_hyper
+    n = comp.shape[0]
+    cand = np.reshape(cand, (-1, comp.shape[1]))
+    best = np.min(vals)
+    Lt = spla.cholesky(cov(kind, tamp2, tls, comp) + tnoise * np.eye(n), lower=True)
+    ta = spla.cho_solve((Lt, True), durs_log - tmean)
+    ftm = np.exp(np.dot(cov(kind, tamp2, tls, comp, cand).T, ta) + tmean)      # (1,)
+    gKt = np.squeeze(grad_kernel(kind, tls, comp, cand), axis=1)                # (N,D)
+    L = spla.cholesky(cov(kind, amp2, ls, comp) + noise * np.eye(n), lower=True)
+    Kx = cov(kind, amp2, ls, comp, cand)
+    gK = np.squeeze(grad_kernel(kind, ls, comp, cand), axis=1)
+    alpha = spla.cho_solve((L, True), vals - mean)
+    beta = spla.solve_triangular(L, Kx, lower=True)
+    m = np.dot(Kx.T, alpha) + mean
+    v = amp2 * (1 + JITTER) - np.sum(beta ** 2, axis=0)
+    s = np.sqrt(v)
+    u = (best - m) / s
+    cdf, pdf = sps.norm.cdf(u), sps.norm.pdf(u)
+    ei = s * (u * cdf + pdf)
+    f = -np.sum(ei / ftm)
+    gtm = np.dot(ta.T, gKt)
+    gx_m = np.dot(alpha.T, gK)
+    gx_v = np.dot(-2 * spla.cho_solve((L, True), Kx).T, gK)
+    g = 0.5 * amp2 * (gx_m * (-cdf) + gx_v * (0.5 * pdf / s))
+    gtm = 0.5 * tamp2 * gtm * ftm
+    g = (ftm * g - ei * gtm) / (ftm ** 2)
+    return f, g.flatten()
+
+
+def grad_optimize_ei_per_s_over_hypers(kind, hyper_samples, time_hyper_samples, cand, comp, vals, durs_log):
+    """Sum over sample pairs i = 0..len(hyper_samples)-1 (PSEC:321-349; time samples indexed from the OLDEST)."""
+    f, g = 0.0, np.zeros(np.size(cand))
+    for h, th in zip(hyper_samples, time_hyper_samples):
+        fi, gi = grad_optimize_ei_per_s(kind, h, th, cand, comp, vals, durs_log)
+        f, g = f + fi, g + gi
+    return f, g

@@ -59,6 +59,7 @@ for _t in ("f32", "f64"):
         "smk_cross_mean_" + _t: ([_i] * 7 + [_p] * 7 + [_i, _p], _i),
         "smk_ei_sweep_" + _t: ([_i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p], _i),
         "smk_topk_" + _t: ([_i, _i, _p, _p, _p, _p, _sz, _p], _i),
+        "smk_ei_grad_terms_" + _t: ([_i] * 7 + [_p] * 8, _i),
     })
 
 

@@ -1,0 +1,100 @@
+"""Compute backend of the chooser plugins: everything numerical that ``next()`` needs, on the GPU.
+
+    loglik(kind, comp, vals)                      -> callable(mean, noise, amp2, ls) -> float   (float64, f2)
+    grid_state(kind, hyper_samples, comp, pend, vals, normals, time_hs, durs_log) -> state
+    ei_matrix(state, cand)                        -> (M, S) float64 numpy                        (OPT:331-341)
+    top_mean_ei(state, cand, k)                   -> indices of the k largest mean-EI candidates, ascending (OPT:270, 294)
+    refine_context(...)                           -> object with value_grad(x)                   (f1, OPT:360-525)
+
+The chooser classes only talk to this interface, so the host logic (RNG order, state files, return protocol)
+can be unit-tested on a CPU-only box with a stand-in backend supplied by the test; the product always constructs
+``DeviceBackend`` and raises if CUDA / the shared library is missing.
+
+Multi-GPU: when torch.distributed is initialised (one process per GPU, NCCL), the hyper-samples of the grid pass are
+sharded round-robin over ranks and combined with ONE all-reduce of the per-candidate EI sum (parallel.py); the MCMC
+chain and the L-BFGS refinement are replicated (same seeds -> identical on every rank).
+"""
+import numpy as np
+import torch
+
+from . import parallel
+from .engine import GPEIEngine, _ceil
+
+
+class _GridState(object):
+    pass
+
+
+class DeviceBackend(object):
+    name = "b200"
+
+    def __init__(self, device=None, refine_dtype="float64"):
+        if device is None and torch.cuda.is_available():
+            rank, world = parallel.world()
+            device = "cuda:%d" % (torch.cuda.current_device() if world == 1 else rank % torch.cuda.device_count())
+        self.eng32 = GPEIEngine(device=device, dtype=torch.float32)
+        self.eng64 = GPEIEngine(device=device, dtype=torch.float64)
+        self.refine_eng = self.eng64 if refine_dtype == "float64" else self.eng32
+
+    # ---- f2
+    def loglik(self, kind, comp, vals):
+        return self.eng64.loglik(kind, comp, vals)
+
+    # ---- grid pass
+    def grid_state(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None,
+                   durs_log=None):
+        """Factors all (local) hyper-samples once; reused by both grid passes of next() (OPT:269, OPT:293)."""
+        eng = self.eng32
+        rank, world = parallel.world()
+        S = len(hyper_samples)
+        mine = parallel.shard(S, rank, world)
+        st = _GridState()
+        st.kind, st.S, st.mine = kind, S, mine
+        st.args = (comp, pend, vals, normals, durs_log)
+        st.hs = [hyper_samples[s] for s in mine]
+        st.ths = None if time_hyper_samples is None else [time_hyper_samples[s] for s in mine]
+        P = 0 if pend is None else pend.shape[0]
+        F = 1 if P == 0 else normals.shape[1]
+        chunk = eng.max_samples_per_chunk(_ceil(comp.shape[0] + P, 128), _ceil(200000, 128), F)
+        st.preps = None
+        if st.hs and len(st.hs) <= chunk:            # everything resident: prepare once, sweep many
+            st.preps = eng.prepare(kind, st.hs, comp, pend, vals, normals, st.ths, durs_log)
+            st.preps.fac.check_pd()
+        return st
+
+    def _local(self, st, cand, want_matrix):
+        eng = self.eng32
+        ldm = _ceil(cand.shape[0], 128)
+        if not st.hs:
+            return None, torch.zeros((ldm,), dtype=eng.dtype, device=eng.device)
+        if st.preps is not None:
+            return eng.ei_prepared(st.preps, eng.to_dev(cand), want_matrix, None)
+        comp, pend, vals, normals, durs_log = st.args
+        ei, ei_sum, _ = eng.ei_over_hypers_device(st.kind, st.hs, comp, pend, cand, vals, normals, st.ths, durs_log,
+                                                  want_matrix=want_matrix)
+        return ei, ei_sum
+
+    def ei_matrix(self, st, cand):
+        M = cand.shape[0]
+        ei, _ = self._local(st, cand, True)
+        rank, world = parallel.world()
+        if world == 1:
+            return ei[:, :M].t().contiguous().double().cpu().numpy()
+        full = torch.zeros((st.S, _ceil(M, 128)), dtype=self.eng32.dtype, device=self.eng32.device)
+        if ei is not None:
+            full[st.mine] = ei
+        parallel.allreduce_sum_(full)                # columns are disjoint across ranks
+        return full[:, :M].t().contiguous().double().cpu().numpy()
+
+    def top_mean_ei(self, st, cand, k):
+        M = cand.shape[0]
+        _, ei_sum = self._local(st, cand, False)
+        parallel.allreduce_sum_(ei_sum)              # the single exchange of the path
+        idx, _ = self.eng32.topk(ei_sum, M, k)       # argsort / argmax of the mean == of the sum
+        return idx.cpu().numpy().astype(int)
+
+    # ---- f1
+    def refine_context(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None,
+                       durs_log=None):
+        return self.refine_eng.refine_context(kind, hyper_samples, comp, pend, vals, normals, time_hyper_samples,
+                                              durs_log)

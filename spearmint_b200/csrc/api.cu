@@ -39,6 +39,9 @@ template <typename T>
 int ei_sweep(int, int, int, const T*, const T*, int, const T*, const T*, T*, T*, cudaStream_t);
 template <typename T>
 int topk(int, int, const T*, int*, T*, void*, size_t, cudaStream_t);
+template <typename T>
+int ei_grad_terms(int, int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, T*,
+                  cudaStream_t);
 size_t topk_workspace_bytes(int, int);
 size_t predict_workspace_bytes_any(int, int);
 
@@ -127,6 +130,19 @@ int smk_topk_f32(int M, int k, const float* score, int* idx_out, float* val_out,
 int smk_topk_f64(int M, int k, const double* score, int* idx_out, double* val_out, void* workspace,
                  size_t workspace_bytes, void* stream) {
   return topk<double>(M, k, score, idx_out, val_out, workspace, workspace_bytes, ST(stream));
+}
+
+int smk_ei_grad_terms_f32(int kind, int N, int Npad, int D, int S, int Q, int F, const float* X, const float* xq,
+                          const float* inv_ls, const float* amp2, const float* alpha, const float* gamma,
+                          float* out, void* stream) {
+  if (kind == SMK_SE) return -1;
+  return ei_grad_terms<float>(kind, N, Npad, D, S, Q, F, X, xq, inv_ls, amp2, alpha, gamma, out, ST(stream));
+}
+int smk_ei_grad_terms_f64(int kind, int N, int Npad, int D, int S, int Q, int F, const double* X, const double* xq,
+                          const double* inv_ls, const double* amp2, const double* alpha, const double* gamma,
+                          double* out, void* stream) {
+  if (kind == SMK_SE) return -1;
+  return ei_grad_terms<double>(kind, N, Npad, D, S, Q, F, X, xq, inv_ls, amp2, alpha, gamma, out, ST(stream));
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ Mirrors, per batch of hyper-samples, what the reference does one sample at a tim
 
     cov_build -> potrf -> chol_solve (alpha) -> predict (mu, var) -> ei_sweep
 
-HBM layout (T = float32 on the production path, float64 for log-likelihoods / logic tests):
+HBM layout (T = float32 on the grid path, float64 for log-likelihoods / refinement / logic tests):
     X        [N][D]            observed (or observed+pending) inputs, row-major
     C        [M][D]            candidates
     hypers   inv_ls[S][D], amp2[S], noise[S], mean[S]
@@ -20,10 +20,13 @@ torch provides the allocator and the stream only.  Nothing here falls back to th
 import ctypes as C
 
 import numpy as np
+import scipy.stats as sps
 import torch
 
 from . import _lib
 from ._lib import KINDS, check, fn, ptr
+
+JITTER = 1e-6   # OPT:209-210
 
 
 def _ceil(x, m):
@@ -47,22 +50,23 @@ class HyperBatch(object):
         self.S, self.D = S, D
         self.mean, self.noise, self.amp2 = dev[:S], dev[S:2 * S], dev[2 * S:3 * S]
         self.inv_ls = dev[3 * S:].view(S, D)
-        self.host_mean, self.host_noise, self.host_amp2 = mean, noise, amp2
+        self.host_mean, self.host_noise, self.host_amp2, self.host_ls = mean, noise, amp2, ls
+        self.nbytes = host.size * (8 if dtype == torch.float64 else 4)
 
 
 class Factor(object):
     """Batched Cholesky factors of K_s = amp2_s (k + 1e-6 I) + noise_s I for S hyper-samples."""
 
-    def __init__(self, eng, kind, X, hb):
+    def __init__(self, eng, kind, X, hb, L=None, winv=None, info=None):
         self.eng, self.kind, self.hb = eng, kind, hb
         self.X = X
         self.N, self.D = X.shape
         self.Npad = _ceil(self.N, 128)
         S, dt, dev = hb.S, eng.dtype, eng.device
         NB = eng.NB
-        self.L = torch.empty((S, self.Npad, self.Npad), dtype=dt, device=dev)
-        self.winv = torch.empty((S, self.Npad // NB, NB, NB), dtype=dt, device=dev)
-        self.info = torch.zeros((S,), dtype=torch.int32, device=dev)
+        self.L = L if L is not None else torch.empty((S, self.Npad, self.Npad), dtype=dt, device=dev)
+        self.winv = winv if winv is not None else torch.empty((S, self.Npad // NB, NB, NB), dtype=dt, device=dev)
+        self.info = info if info is not None else torch.zeros((S,), dtype=torch.int32, device=dev)
         st = eng.stream()
         check(fn("smk_cov_build", dt)(KINDS[kind], self.N, self.N, self.D, S, ptr(X), None, ptr(hb.inv_ls),
                                       ptr(hb.amp2), ptr(hb.noise), ptr(self.L), self.Npad, st), "cov_build")
@@ -94,8 +98,22 @@ class Factor(object):
         return alpha, sld, quad
 
 
+class _LeadingView(object):
+    """A Factor-like view exposing only the first N rows of a joint factor's inputs (for cross_mean)."""
+
+    def __init__(self, fac, X, N):
+        self.hb, self.X, self.N, self.D, self.Npad = fac.hb, X, N, fac.D, fac.Npad
+        self.L, self.winv = fac.L, fac.winv
+
+
+class Prepared(object):
+    """Everything about one chunk of hyper-samples that does not depend on the candidate set:
+    factors, alpha (one column, or F fantasy columns), bests, optional time-GP factor and alpha."""
+    pass
+
+
 class GPEIEngine(object):
-    """One engine per process / GPU.  ``dtype`` float32 is the product path."""
+    """One engine per process / GPU and element type.  float32 is the grid path."""
 
     def __init__(self, device=None, dtype=torch.float32):
         if not torch.cuda.is_available():
@@ -110,6 +128,7 @@ class GPEIEngine(object):
         self.last = {}
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
 
+    # ------------------------------------------------------------------ timing helpers
     def _t0(self):
         if self.timers is None:
             return None
@@ -153,8 +172,8 @@ class GPEIEngine(object):
     def hypers(self, hyper_samples, kind):
         return HyperBatch(hyper_samples, kind, self.device, self.dtype)
 
-    def factor(self, kind, X, hb):
-        return Factor(self, kind, X, hb)
+    def factor(self, kind, X, hb, **kw):
+        return Factor(self, kind, X, hb, **kw)
 
     def cov(self, kind, hb, X, Y=None):
         """Batched chooser.cov (OPT:207-212): returns [S][N][N] (self, jitter included, no noise) or [S][N][M]."""
@@ -214,74 +233,51 @@ class GPEIEngine(object):
         check(fn("smk_topk", dt)(M, k, ptr(score), ptr(idx), ptr(val), ptr(ws), nb, self.stream()), "topk")
         return idx, val
 
-    # ------------------------------------------------------------------ whole path
-    def ei_over_hypers_device(self, kind, hyper_samples, comp, pend, cand, vals, normals=None,
-                              time_hyper_samples=None, durs_log=None, want_matrix=True, inputs_on_device=None):
-        """Runs the batched path; returns (ei [S][ldm] or None, ei_sum [ldm], M) as device tensors.
-
-        ``normals`` (P,F): the fantasy standard normals the reference draws on the host (OPT:588-589).
-        ``time_hyper_samples`` + ``durs_log``: EI per second (PSEC:437-548).
-        ``inputs_on_device``: optional dict(X=, C=, y=) of resident tensors (bench 'value' leg)."""
+    # ------------------------------------------------------------------ candidate-independent state
+    def prepare(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None, durs_log=None,
+                resident=None):
+        """Factor + alpha (+ fantasies, + time GP) for one chunk of hyper-samples.  ``resident`` = dict(X, y, best,
+        hb) of tensors already in HBM (the bench's `value` leg)."""
+        p = Prepared()
+        p.kind = kind
         P = 0 if pend is None else int(pend.shape[0])
-        S = len(hyper_samples)
-        if inputs_on_device is not None:
-            Xo, Cd, yd = inputs_on_device["X"], inputs_on_device["C"], inputs_on_device["y"]
-            best_val = inputs_on_device["best"]
+        if resident is not None:
+            Xo, yd, best_val = resident["X"], resident["y"], resident["best"]
+            hb = resident.get("hb") or self.hypers(hyper_samples, kind)
         else:
-            Xo, Cd, yd = self.to_dev(comp), self.to_dev(cand), self.to_dev(vals)
-            best_val = float(np.min(vals))
-        N, D = Xo.shape
-        M = Cd.shape[0]
-        ldm = _ceil(M, 128)
-        Fn = 1 if P == 0 else int(normals.shape[1])
-        chunk = self.max_samples_per_chunk(_ceil(N + P, 128), ldm, Fn)
-        ei_sum = torch.zeros((ldm,), dtype=self.dtype, device=self.device)
-        ei_all = torch.empty((S, ldm), dtype=self.dtype, device=self.device) if want_matrix else None
-        for s0 in range(0, S, chunk):
-            hs = hyper_samples[s0:s0 + chunk]
-            if inputs_on_device is not None and inputs_on_device.get("hb") is not None and chunk >= S:
-                hb = inputs_on_device["hb"]
-            else:
-                hb = self.hypers(hs, kind)
-            log_time = None
-            if time_hyper_samples is not None:
-                thb = self.hypers(time_hyper_samples[s0:s0 + chunk], kind)
-                tfac = self.factor(kind, Xo, thb)
-                tfac.check_pd()
-                ta, _, _ = tfac.solve(self.to_dev(durs_log), F=1)
-                log_time = self.cross_mean(kind, tfac, Cd, ta, 1).view(thb.S, ldm)
-                del tfac
-            if P == 0:
-                t = self._t0()
-                fac = self.factor(kind, Xo, hb)
-                self._t1("cov_potrf", t)
-                t = self._t0()
-                alpha, _, _ = fac.solve(yd, F=1)
-                self._t1("chol_solve", t)
-                t = self._t0()
-                mu, var, _ = self.predict(kind, fac, Cd, alpha)
-                self._t1("predict", t)
-                best = torch.full((hb.S, 1), best_val, dtype=self.dtype, device=self.device)
-                t = self._t0()
-                ei, _ = self.ei_sweep(M, hb.S, 1, mu, var, ldm, best, log_time, want_matrix, ei_sum)
-                self._t1("ei_sweep", t)
-                fac.check_pd()   # one host sync per chunk, after everything is queued
-            else:
-                ei = self._pending_chunk(kind, hb, Xo, self.to_dev(pend), Cd, yd, np.asarray(vals, float),
-                                         np.asarray(normals, float), log_time, M, ldm, want_matrix, ei_sum)
-            if want_matrix:
-                ei_all[s0:s0 + hb.S] = ei
-            self.last = dict(N=N, M=M, D=D, S=S, P=P, chunk=chunk)
-        return ei_all, ei_sum, M
+            Xo, yd, best_val = self.to_dev(comp), self.to_dev(vals), float(np.min(vals))
+            hb = self.hypers(hyper_samples, kind)
+        p.hb, p.N, p.P, p.S = hb, Xo.shape[0], P, hb.S
+        p.time = None
+        if time_hyper_samples is not None:          # PSEC:442-459
+            thb = self.hypers(time_hyper_samples, kind)
+            tfac = self.factor(kind, Xo, thb)
+            ta, _, _ = tfac.solve(self.to_dev(durs_log), F=1)
+            p.time = (tfac, ta)
+        if P == 0:
+            t = self._t0()
+            fac = self.factor(kind, Xo, hb)
+            self._t1("cov_potrf", t)
+            t = self._t0()
+            alpha, _, _ = fac.solve(yd, F=1)
+            self._t1("chol_solve", t)
+            p.fac, p.alpha, p.F = fac, alpha, 1
+            p.bests = torch.full((hb.S, 1), best_val, dtype=self.dtype, device=self.device)
+            p.bests_host = np.full((hb.S, 1), best_val)
+            p.pred_alpha = alpha.view(hb.S, fac.Npad)
+        else:
+            self._prepare_pending(p, kind, hb, Xo, self.to_dev(pend), yd, np.asarray(vals, float),
+                                  np.asarray(normals, float))
+        return p
 
-    def _pending_chunk(self, kind, hb, Xo, Pd, Cd, yd, vals, normals, log_time, M, ldm, want_matrix, ei_sum):
-        """Pending-fantasy branch (OPT:558-619) for one chunk of hyper-samples.
+    def _prepare_pending(self, p, kind, hb, Xo, Pd, yd, vals, normals):
+        """Pending-fantasy prologue (OPT:558-603) for one chunk of hyper-samples.
 
-        The joint (N+P) factor, all big solves and the candidate sweep run on the device; the P x P
-        conditional of the pending points (P <= max_concurrent, a handful) and the fantasy draw use the
-        host in float64 with the caller's normals, so the host RNG order is the reference's."""
+        The joint (N+P) factor and all big solves run on the device; the P x P conditional of the pending points
+        (P <= max_concurrent, a handful) and the fantasy draw use the host in float64 with the caller's normals, so
+        the host RNG order is the reference's."""
         N, P, F = Xo.shape[0], Pd.shape[0], normals.shape[1]
-        S, dt = hb.S, self.dtype
+        S = hb.S
         Xj = torch.cat([Xo, Pd], dim=0).contiguous()
         fac = self.factor(kind, Xj, hb)
         fac.check_pd()
@@ -304,11 +300,62 @@ class GPEIEngine(object):
             bests[s] = np.minimum(vals.min(), pf.min(axis=0))                     # OPT:597
         fant_d = self.to_dev(fant)                                                # [S][F][N+P]
         alpha_f, _, _ = fac.solve(fant_d, F=F, y_stride=F * (N + P), ldy=N + P)   # OPT:603
-        zero_alpha = torch.zeros((S, fac.Npad), dtype=dt, device=self.device)
-        _, var, _ = self.predict(kind, fac, Cd, zero_alpha)                        # OPT:605, 610
-        mu = self.cross_mean(kind, fac, Cd, alpha_f, F)                            # OPT:609
-        ei, _ = self.ei_sweep(M, S, F, mu, var, ldm, self.to_dev(bests), log_time, want_matrix, ei_sum)
-        return ei
+        p.fac, p.alpha, p.F = fac, alpha_f, F
+        p.bests, p.bests_host = self.to_dev(bests), bests
+        p.pred_alpha = torch.zeros((S, fac.Npad), dtype=self.dtype, device=self.device)
+
+    def ei_prepared(self, p, Cd, want_matrix=True, ei_sum=None):
+        """EI of every candidate in Cd for every sample of a Prepared chunk.  Returns (ei [S][ldm] | None, ei_sum)."""
+        kind, fac, hb = p.kind, p.fac, p.hb
+        M = Cd.shape[0]
+        ldm = _ceil(M, 128)
+        log_time = None
+        if p.time is not None:
+            tfac, ta = p.time
+            log_time = self.cross_mean(kind, tfac, Cd, ta, 1).view(tfac.hb.S, ldm)
+        t = self._t0()
+        mu, var, _ = self.predict(kind, fac, Cd, p.pred_alpha)                     # OPT:544-548 / 605-610
+        self._t1("predict", t)
+        if p.P > 0:
+            mu = self.cross_mean(kind, fac, Cd, p.alpha, p.F)                      # OPT:609
+        else:
+            mu = mu.view(hb.S, 1, ldm)
+        t = self._t0()
+        out = self.ei_sweep(M, hb.S, p.F, mu, var, ldm, p.bests, log_time, want_matrix, ei_sum)
+        self._t1("ei_sweep", t)
+        return out
+
+    # ------------------------------------------------------------------ whole path
+    def ei_over_hypers_device(self, kind, hyper_samples, comp, pend, cand, vals, normals=None,
+                              time_hyper_samples=None, durs_log=None, want_matrix=True, inputs_on_device=None):
+        """Runs the batched path; returns (ei [S][ldm] or None, ei_sum [ldm], M) as device tensors.
+
+        ``normals`` (P,F): the fantasy standard normals the reference draws on the host (OPT:588-589).
+        ``time_hyper_samples`` + ``durs_log``: EI per second (PSEC:437-548).
+        ``inputs_on_device``: optional dict(X=, C=, y=, best=, hb=) of resident tensors (bench `value` leg)."""
+        P = 0 if pend is None else int(pend.shape[0])
+        S = len(hyper_samples)
+        res = inputs_on_device
+        Cd = res["C"] if res is not None else self.to_dev(cand)
+        N = res["X"].shape[0] if res is not None else comp.shape[0]
+        M = Cd.shape[0]
+        ldm = _ceil(M, 128)
+        Fn = 1 if P == 0 else int(normals.shape[1])
+        chunk = self.max_samples_per_chunk(_ceil(N + P, 128), ldm, Fn)
+        ei_sum = torch.zeros((ldm,), dtype=self.dtype, device=self.device)
+        ei_all = torch.empty((S, ldm), dtype=self.dtype, device=self.device) if want_matrix else None
+        for s0 in range(0, S, chunk):
+            r = res if (res is not None and chunk >= S) else (dict(res, hb=None) if res is not None else None)
+            prep = self.prepare(kind, hyper_samples[s0:s0 + chunk], comp, pend, vals, normals,
+                                None if time_hyper_samples is None else time_hyper_samples[s0:s0 + chunk],
+                                durs_log, resident=r)
+            ei, _ = self.ei_prepared(prep, Cd, want_matrix, ei_sum)
+            prep.fac.check_pd()     # one host sync per chunk, after everything is queued
+            if want_matrix:
+                ei_all[s0:s0 + prep.S] = ei
+            del prep
+        self.last = dict(N=N, M=M, S=S, P=P, chunk=chunk)
+        return ei_all, ei_sum, M
 
     def ei_over_hypers(self, kind, hyper_samples, comp, pend, cand, vals, normals=None,
                        time_hyper_samples=None, durs_log=None):
@@ -317,10 +364,110 @@ class GPEIEngine(object):
                                               time_hyper_samples, durs_log, want_matrix=True)
         return ei[:, :M].t().contiguous().double().cpu().numpy()
 
+    # ------------------------------------------------------------------ f2: GP log marginal likelihood
+    def loglik(self, kind, comp, vals):
+        return LogLik(self, kind, comp, vals)
 
-class _LeadingView(object):
-    """A Factor-like view exposing only the first N rows of a joint factor's inputs (for cross_mean)."""
+    # ------------------------------------------------------------------ f1: cached-factor EI value + gradient
+    def refine_context(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None,
+                       durs_log=None):
+        return RefineContext(self, kind, hyper_samples, comp, pend, vals, normals, time_hyper_samples, durs_log)
 
-    def __init__(self, fac, X, N):
-        self.hb, self.X, self.N, self.D, self.Npad = fac.hb, X, N, fac.D, fac.Npad
-        self.L, self.winv = fac.L, fac.winv
+
+class LogLik(object):
+    """-sum(log diag chol K) - 0.5 (y-mu)' K^-1 (y-mu) for ONE hyper-parameter setting per call -- the data term of
+    every slice-sampler log-probability (OPT:635-640, 658-661, 689-692).  Buffers are allocated once; a call is
+    cov_build + potrf + forward substitution, then one small device->host read (the sampler needs the scalar to
+    decide its next step)."""
+
+    def __init__(self, eng, kind, comp, vals):
+        self.eng, self.kind = eng, kind
+        self.X = eng.to_dev(comp)
+        self.y = eng.to_dev(vals)
+        self.N, self.D = self.X.shape
+        Npad = _ceil(self.N, 128)
+        dt, dev = eng.dtype, eng.device
+        self.L = torch.empty((1, Npad, Npad), dtype=dt, device=dev)
+        self.winv = torch.empty((1, Npad // eng.NB, eng.NB, eng.NB), dtype=dt, device=dev)
+        self.info = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.calls = 0
+
+    def __call__(self, mean, noise, amp2, ls):
+        eng = self.eng
+        hb = eng.hypers([(mean, noise, amp2, np.asarray(ls, dtype=float))], self.kind)
+        fac = Factor(eng, self.kind, self.X, hb, L=self.L, winv=self.winv, info=self.info)
+        _, sld, quad = fac.solve(self.y, F=1, want_alpha=False, want_logdet=True, want_quad=True)
+        out = torch.cat([sld.double().view(1), quad.double().view(1), self.info.double()]).cpu().numpy()
+        self.calls += 1
+        if out[2] != 0:
+            raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite" % int(out[2]))
+        return -out[0] - 0.5 * out[1]
+
+
+class RefineContext(object):
+    """(f, g) of GPEIOptChooser.grad_optimize_ei_over_hypers (OPT:360-525) / GPEIperSecChooser's (PSEC:321-435) at
+    one point, with the S factors cached (the reference re-factors K for every sample on every evaluation)."""
+
+    def __init__(self, eng, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None,
+                 durs_log=None):
+        if kind == "SE":
+            raise AttributeError("module 'spearmint.gp' has no attribute 'grad_SE'")   # what the reference does, OPT:404
+        self.eng, self.kind = eng, kind
+        self.prep = eng.prepare(kind, hyper_samples, comp, pend, vals, normals, time_hyper_samples, durs_log)
+        self.prep.fac.check_pd()
+        self.pending = self.prep.P > 0
+        self.hb = self.prep.hb
+        self.evals = 0
+
+    def _terms(self, fac, alpha, F, x):
+        """out[S][F+1][D+1] of smk_ei_grad_terms for a single query point."""
+        eng, dt = self.eng, self.eng.dtype
+        hb = fac.hb
+        S, N, D = hb.S, fac.N, fac.D
+        xq = eng.to_dev(np.reshape(x, (1, D)))
+        # kx as right-hand sides: cov(xq, X) -> [S][1][N]
+        kx = torch.empty((S, 1, N), dtype=dt, device=eng.device)
+        check(fn("smk_cov_build", dt)(KINDS[self.kind], 1, N, D, S, ptr(xq), ptr(fac.X), ptr(hb.inv_ls),
+                                      ptr(hb.amp2), None, ptr(kx), N, eng.stream()), "cov_build")
+        gamma, _, _ = fac.solve(kx, F=1, y_stride=N, ldy=N, subtract_mean=False)
+        out = torch.empty((S, 1, F + 1, D + 1), dtype=dt, device=eng.device)
+        check(fn("smk_ei_grad_terms", dt)(KINDS[self.kind], N, fac.Npad, D, S, 1, F, ptr(fac.X), ptr(xq),
+                                          ptr(hb.inv_ls), ptr(hb.amp2), ptr(alpha), ptr(gamma), ptr(out),
+                                          eng.stream()), "ei_grad_terms")
+        return out.double().cpu().numpy()[:, 0]
+
+    def per_sample(self, x):
+        """Per hyper-sample (f_s, g_s) exactly as grad_optimize_ei returns them (OPT:391-525), incl. the 0.5*amp2."""
+        p, hb = self.prep, self.hb
+        F, D = p.F, p.fac.D
+        out = self._terms(p.fac, p.alpha, F, x)                        # (S, F+1, D+1)
+        amp2, mean = hb.host_amp2, hb.host_mean
+        m = out[:, :F, D] + mean[:, None]                              # func_m (S,F)         OPT:417 / 508
+        v = amp2 * (1 + JITTER) - out[:, F, D]                         # func_v (S,)          OPT:418 / 509
+        s = np.sqrt(v)[:, None]
+        u = (p.bests_host - m) / s
+        cdf, pdf = sps.norm.cdf(u), sps.norm.pdf(u)
+        ei = s * (u * cdf + pdf)                                       # (S,F)
+        g_m, g_s2 = -cdf, 0.5 * pdf / s
+        gx_m = out[:, :F, :D]                                          # (S,F,D)
+        gx_v = -2.0 * out[:, F, :D]                                    # (S,D)
+        g = 0.5 * amp2[:, None, None] * (gx_m * g_m[:, :, None] + gx_v[:, None, :] * g_s2[:, :, None])
+        self.evals += 1
+        if not self.pending:
+            f_s, g_s, ei_s = -ei.sum(axis=1), g[:, 0, :], ei[:, 0]
+        else:
+            f_s, g_s, ei_s = -ei.mean(axis=1), g.mean(axis=1), ei.mean(axis=1)
+        if p.time is not None:                                         # PSEC:351-435
+            tfac, ta = p.time
+            tout = self._terms(tfac, ta, 1, x)                         # (S, 2, D+1)
+            thb = tfac.hb
+            ftm = np.exp(tout[:, 0, D] + thb.host_mean)                # func_time_m
+            gt = 0.5 * thb.host_amp2[:, None] * tout[:, 0, :D] * ftm[:, None]
+            g_s = (ftm[:, None] * g_s - ei_s[:, None] * gt) / (ftm[:, None] ** 2)
+            f_s = -(ei_s / ftm)
+        return f_s, g_s
+
+    def value_grad(self, x):
+        """Sum over hyper-samples (OPT:360-388)."""
+        f_s, g_s = self.per_sample(np.asarray(x, dtype=float))
+        return float(f_s.sum()), g_s.sum(axis=0).flatten()

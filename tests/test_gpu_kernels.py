@@ -124,8 +124,12 @@ def test_predict_moments(engines, kind, prec, D, N, M):
             np.testing.assert_allclose(mu[s], m_ref, rtol=1e-8, atol=1e-9)
             np.testing.assert_allclose(var[s], v_ref, rtol=1e-7, atol=1e-9)
         else:
-            np.testing.assert_allclose(mu[s], m_ref, rtol=1e-4, atol=2e-4)       # mean rtol 1e-4
-            np.testing.assert_allclose(var[s], v_ref, rtol=1e-3, atol=2e-4 * h[2])
+            # mean rtol 1e-4.  The absolute floor is eps_fp32 * sum_i |Kx_i alpha_i| (fp32 rounding of
+            # Kx itself): ~2e-4 for Matern, ~1e-3 for the far worse conditioned SE-type kernels (cond ~ N*amp2/noise
+            # with a super-exponential spectrum).  EI-level parity is asserted separately in test_gpu_golden.py.
+            floor = 1e-3 if kind in ("SE", "ARDSE") else 2e-4
+            np.testing.assert_allclose(mu[s], m_ref, rtol=1e-4, atol=floor)
+            np.testing.assert_allclose(var[s], v_ref, rtol=1e-3, atol=floor * h[2])
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
