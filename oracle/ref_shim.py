@@ -97,3 +97,15 @@ def load():
     _loaded.update(gp=gp, util=util, Locker=locker, sobol_lib=sobol,
                    OPT=opt, PSEC=psec, GPEI=gpei)
     return _loaded
+
+
+def load_lite():
+    """The reference's spearmint-lite controller (spearmint-lite/spearmint-lite.py) with its own ExperimentGrid,
+    executed under the same py3 rewrites.  Returns the module (main_controller, GridMap...)."""
+    load()
+    lite_dir = os.path.join(REF_ROOT, "spearmint-lite")
+    if "ExperimentGrid" not in sys.modules or not getattr(sys.modules["ExperimentGrid"], "_lite", False):
+        sys.modules["sobol_lib"] = _exec_module("sobol_lib", os.path.join(lite_dir, "sobol_lib.py"))
+        eg = _exec_module("ExperimentGrid", os.path.join(lite_dir, "ExperimentGrid.py"))
+        eg._lite = True
+    return _exec_module("spearmint_lite", os.path.join(lite_dir, "spearmint-lite.py"))
