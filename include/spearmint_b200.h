@@ -96,6 +96,23 @@ int smk_predict_f64(int kind, int N, int Npad, int M, int D, int S, const double
                     const double* winv, const double* alpha, double* mu, double* var, int ldm,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- (4-tc) fused predict on the tensor cores (tcgen05 + TMEM + TMA, 3xTF32 split; float32 only)
+ * Same outputs as smk_predict_f32 (OPT:536, 544, 547-548).  Two steps so that the factor-only part is done once:
+ *   smk_trtri_split_f32 : Linv = L^-1 (explicit inverse of the blocked factor) split into tf32 hi / lo parts,
+ *                         each [S][Np][Np] with Np = smk_tc_np(N) (N rounded up to 256), zero above the diagonal.
+ *   smk_predict_tc_f32  : cross-covariance (candidate-major, split) -> D = Kxt * Linv^T on tcgen05 -> var, mu.
+ * alpha: [S][Npad_alpha] (first right-hand side).  dbg_beta (tests only, may be NULL): [S][Mc][Np] dump of
+ * beta^T for a single-chunk call.                                                                              */
+int smk_tc_np(int N);
+size_t smk_trtri_workspace_bytes(int Np, int S);
+int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi,
+                        float* linv_lo, void* workspace, size_t workspace_bytes, void* stream);
+size_t smk_predict_tc_workspace_bytes(int Np, int M, int S);
+int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
+                       const float* inv_ls, const float* amp2, const float* mean, const float* linv_hi,
+                       const float* linv_lo, const float* alpha, int Npad_alpha, float* mu, float* var, int ldm,
+                       void* workspace, size_t workspace_bytes, float* dbg_beta, void* stream);
+
 /* ---- (4b) cross mean only: mu[s][f][j] = cov(X, C_j)' alpha[s][f] + mean[s]
  *          time-GP mean of EI-per-second (PSEC:442-459) and fantasy means (OPT:609).
  * alpha: [S][F][Npad]; mu: [S][F][ldm].                                                         */

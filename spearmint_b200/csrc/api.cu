@@ -43,6 +43,12 @@ template <typename T>
 int ei_grad_terms(int, int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, T*,
                   cudaStream_t);
 size_t topk_workspace_bytes(int, int);
+int tc_np(int);
+size_t trtri_workspace_bytes(int, int);
+int trtri_split(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
+size_t predict_tc_workspace_bytes(int, int, int);
+int predict_tc(int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
+               const float*, const float*, const float*, int, float*, float*, int, void*, size_t, float*, cudaStream_t);
 size_t predict_workspace_bytes_any(int, int);
 
 }  // namespace smk
@@ -100,6 +106,21 @@ int smk_predict_f64(int kind, int N, int Npad, int M, int D, int S, const double
                     size_t workspace_bytes, void* stream) {
   return predict<double>(kind, N, Npad, M, D, S, X, C, inv_ls, amp2, mean, L, winv, alpha, mu, var, ldm, workspace,
                          workspace_bytes, ST(stream));
+}
+
+int smk_tc_np(int N) { return tc_np(N); }
+size_t smk_trtri_workspace_bytes(int Np, int S) { return trtri_workspace_bytes(Np, S); }
+int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi, float* linv_lo,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  return trtri_split(Npad, Np, S, L, winv, linv_hi, linv_lo, workspace, workspace_bytes, ST(stream));
+}
+size_t smk_predict_tc_workspace_bytes(int Np, int M, int S) { return predict_tc_workspace_bytes(Np, M, S); }
+int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
+                       const float* inv_ls, const float* amp2, const float* mean, const float* linv_hi,
+                       const float* linv_lo, const float* alpha, int Npad_alpha, float* mu, float* var, int ldm,
+                       void* workspace, size_t workspace_bytes, float* dbg_beta, void* stream) {
+  return predict_tc(kind, N, Np, M, D, S, X, C, inv_ls, amp2, mean, linv_hi, linv_lo, alpha, Npad_alpha, mu, var, ldm,
+                    workspace, workspace_bytes, dbg_beta, ST(stream));
 }
 
 int smk_cross_mean_f32(int kind, int N, int Npad, int M, int D, int S, int F, const float* X, const float* C,

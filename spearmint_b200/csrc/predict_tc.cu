@@ -1,0 +1,531 @@
+// predict_tc.cu -- tensor-core (tcgen05 / TMEM / TMA) version of the fused predict stage.
+//
+// Same contract as predict.cu (reference spans OPT:536, 544, 547-548), different dataflow:
+//   1. trtri   : Linv = L^-1 (explicit, blocked, float32 SIMT) -- removes the row-block dependency chain of the
+//                triangular solve so that  beta = Linv * Kx  is one dense (lower-trapezoidal) contraction.
+//   2. split   : Linv -> (hi, lo) with hi = tf32-truncated value, lo = x - hi   (exact in float32)
+//   3. kxt     : Kxt[s][c][n] = amp2 k(X_n, C_c) for a chunk of candidates, written candidate-major (n contiguous,
+//                i.e. K-major for the MMA) already split into (hi, lo); fused  mu[c] = sum_n alpha[n] Kx[c][n] + mean.
+//   4. mma     : per (sample, 128-candidate tile, row-group pair):  D[c][i] = sum_n Kxt[c][n] * Linv[i][n]
+//                as 3xTF32  (hi*hi + hi*lo + lo*hi)  with tcgen05.mma.kind::tf32, operands staged by TMA
+//                (128B swizzle), accumulators in TMEM (2 x 256 columns, double-buffered against the epilogue);
+//                epilogue = tcgen05.ld + per-lane sum of squares (one candidate per TMEM lane: no cross-thread
+//                reduction), partial sums per row-group pair.
+//   5. finish  : var = amp2 (1 + 1e-6) - sum_p partial[p]
+// Why 3xTF32: a single TF32 pass (10-bit mantissa) cannot resolve var = amp2 - |beta|^2 (it goes negative on the
+// reference's own test problems); hi/lo splitting restores ~2^-21 operand accuracy at 3 MMAs
+// per product, i.e. 1/6 of the dense bf16 tensor peak is the ceiling of this formulation.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace smk {
+
+// ================================================================================================= trtri (SIMT)
+// X = L^-1 by block columns: X_JJ = W_JJ;  X_IJ = -W_II * sum_{J<=K<I} L_IK X_KJ.   grid = (nblk, S).
+__global__ void __launch_bounds__(256, 2) trtri_kernel(int Npad, int ldx, const float* __restrict__ L,
+                                                        const float* __restrict__ winv, float* X) {
+  using C = Cfg<float>;
+  constexpr int NB = C::NB, TM = C::TM, TN = C::TN;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<float>& sm = *reinterpret_cast<TileSmem<float>*>(smem_raw);
+  float (*Ts)[NB + kPad] = reinterpret_cast<float (*)[NB + kPad]>(smem_raw + sizeof(TileSmem<float>));
+  const int nblk = Npad / NB, J = blockIdx.x, s = blockIdx.y;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const float* Ls = L + (long)s * Npad * Npad;
+  const float* Ws = winv + (long)s * nblk * NB * NB;
+  float* Xs = X + (long)s * ldx * ldx;
+  for (int I = J; I < nblk; ++I) {
+    float acc[TM][TN];
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
+    if (I == J) {
+      const float* W = Ws + (long)J * NB * NB;
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int g = 0; g < TN / 4; ++g) {
+          V4<float> v = ld4(W + (long)tile_row(ty, r) * NB + g * 64 + tx * 4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[r][g * 4 + e] = v.v[e];
+        }
+    } else {
+      TileGemm<float, Lay::KContig, Lay::MContig, true>::run(acc, Ls + (long)I * NB * Npad + (long)J * NB, Npad,
+                                                            Xs + (long)J * NB * ldx + (long)J * NB, ldx,
+                                                            (I - J) * NB, sm);
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int g = 0; g < TN / 4; ++g) {
+          V4<float> v;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
+          st4(&Ts[tile_row(ty, r)][g * 64 + tx * 4], v);
+        }
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
+      TileGemm<float, Lay::KContig, Lay::MContig, false>::run_bsmem(acc, Ws + (long)I * NB * NB, NB, &Ts[0][0],
+                                                                   NB + kPad, NB, sm);
+    }
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int g = 0; g < TN / 4; ++g) {
+        V4<float> v;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
+        st4(Xs + (long)(I * NB + tile_row(ty, r)) * ldx + J * NB + g * 64 + tx * 4, v);
+      }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// hi/lo split of the lower triangle (upper triangle and padding are written as zeros)
+__global__ void split_lower_kernel(int Npad, int ld, long total, const float* __restrict__ X, float* __restrict__ hi,
+                                   float* __restrict__ lo) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  long per = (long)ld * ld;
+  int r = (int)((e % per) / ld), c = (int)(e % ld);
+  float x = (c <= r && r < Npad) ? X[e] : 0.f;
+  float h = tf32_hi(x);
+  hi[e] = h;
+  lo[e] = x - h;
+}
+
+// ================================================================================================= kxt (SIMT)
+// One block = 32 candidates x all n (tiles of 32): Kxt[s][c][n] (hi, lo), mu[s][c].  grid = (Mc/32, S).
+__global__ void __launch_bounds__(256) kxt_kernel(int kind, int N, int Np, int M, int c_begin, int Mc, int D,
+                                                  const float* __restrict__ X, const float* __restrict__ Cc,
+                                                  const float* __restrict__ inv_ls, const float* __restrict__ amp2,
+                                                  const float* __restrict__ mean, const float* __restrict__ alpha,
+                                                  int Npad_alpha, float* __restrict__ khi, float* __restrict__ klo,
+                                                  float* __restrict__ mu, int ldm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* cs = reinterpret_cast<float*>(smem_raw);   // [32][D+1] scaled candidates
+  float* xs = cs + 32 * (D + 1);                    // [32][D+1] scaled X tile
+  float* il = xs + 32 * (D + 1);                    // [D]
+  const int s = blockIdx.y, c0 = blockIdx.x * 32;   // c0 relative to the chunk
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int d = threadIdx.x; d < D; d += 256) il[d] = inv_ls[(long)s * D + d];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * D; e += 256) {
+    int c = e / D, d = e % D;
+    int gc = min(c_begin + c0 + c, M - 1);
+    cs[c * (D + 1) + d] = Cc[(long)gc * D + d] * il[d];
+  }
+  const float a2 = amp2[s];
+  const float* al = alpha + (long)s * Npad_alpha;
+  float macc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n0 = 0; n0 < Np; n0 += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * D; e += 256) {
+      int i = e / D, d = e % D, n = n0 + i;
+      xs[i * (D + 1) + d] = (n < N) ? X[(long)n * D + d] * il[d] : 0.f;
+    }
+    __syncthreads();
+    const int n = n0 + tx;
+    const float an = (n < N) ? al[n] : 0.f;
+    const float* xr = xs + tx * (D + 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = ty + 8 * k;
+      const float* cr = cs + c * (D + 1);
+      float r2 = 0.f;
+      for (int d = 0; d < D; ++d) {
+        float df = xr[d] - cr[d];
+        r2 = fmaf(df, df, r2);
+      }
+      float kv = (n < N) ? a2 * kernel_of_r2<float>(kind, r2) : 0.f;
+      macc[k] = fmaf(an, kv, macc[k]);
+      float h = tf32_hi(kv);
+      long o = ((long)s * Mc + c0 + c) * Np + n;
+      khi[o] = h;
+      klo[o] = kv - h;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v = macc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int gc = c_begin + c0 + ty + 8 * k;
+    if (tx == 0 && gc < M) mu[(long)s * ldm + gc] = v + mean[s];
+  }
+}
+
+// ================================================================================================= tcgen05 kernel
+namespace tc {
+constexpr int BM = 128;        // candidates per tile (TMEM lanes, MMA M)
+constexpr int BN = 256;        // rows of Linv per group (MMA N, TMEM columns per accumulator)
+constexpr int BK = 32;         // k per stage: 32 x 4 B = one 128-byte swizzle row
+constexpr int UK = 8;          // k per tcgen05.mma.kind::tf32
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int B_BYTES = BN * BK * 4;   // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
+constexpr int THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                            uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), LBO unused (=1).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+struct Args {
+  int S, Np, Mc, ntiles, npairs, ngroups, ldp;   // Mc = candidates per chunk (multiple of 128); ldp = partial stride
+  float* partial;                                 // [npairs][S][ldp]
+  float* dbg;                                     // optional [S][Mc][Np] dump of beta^T (tests only)
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                  const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo, Args p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long nitems = (long)p.S * p.ntiles * p.npairs;
+  // item -> (s, tile, pair): consecutive items share (s, tile) so the pair-blocks of one candidate tile run
+  // concurrently on neighbouring SMs and hit L2 for the Kxt slab.
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t hintA = 0x12F0000000000000ull;   // EVICT_FIRST: Kxt is streamed
+      const uint64_t hintB = 0x14F0000000000000ull;   // EVICT_LAST : Linv is re-read by every tile of the sample
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
+        const int pr = (int)(w % p.npairs);
+        const long st = w / p.npairs;
+        const int tile = (int)(st % p.ntiles), s = (int)(st / p.ntiles);
+        for (int h = 0; h < 2; ++h) {
+          const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
+          if (h == 1 && g == pr) break;                 // middle group of an odd count
+          const int nk = (g + 1) * (BN / BK);
+          const int rowA = s * p.Mc + tile * BM, rowB = s * p.Np + g * BN;
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* sb = base + stage * STAGE_BYTES;
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(&mAhi, &full[stage], sb, kc * BK, rowA, hintA);
+            tma_load_2d(&mAlo, &full[stage], sb + A_BYTES, kc * BK, rowA, hintA);
+            tma_load_2d(&mBhi, &full[stage], sb + 2 * A_BYTES, kc * BK, rowB, hintB);
+            tma_load_2d(&mBlo, &full[stage], sb + 2 * A_BYTES + B_BYTES, kc * BK, rowB, hintB);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, buf = 0, bphase = 0;
+      for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
+        const int pr = (int)(w % p.npairs);
+        for (int h = 0; h < 2; ++h) {
+          const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
+          if (h == 1 && g == pr) break;
+          const int nk = (g + 1) * (BN / BK);
+          mbar_wait(&tempty[buf], bphase ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d = tmem_base + buf * BN;
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&full[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
+            const uint64_t ahi = umma_desc(sa), alo = umma_desc(sa + A_BYTES);
+            const uint64_t bhi = umma_desc(sa + 2 * A_BYTES), blo = umma_desc(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t ko = (uint64_t)((k * UK * 4) >> 4);     // advance inside the swizzle atom (16 B units)
+              umma_tf32(d, alo + ko, bhi + ko, (kc | k) ? 1u : 0u);  // small terms first
+              umma_tf32(d, ahi + ko, blo + ko, 1u);
+              umma_tf32(d, ahi + ko, bhi + ko, 1u);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull[buf]);
+          buf ^= 1;
+          if (buf == 0) bphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // epilogue warps 2..5 own TMEM lane quarters (warp % 4)
+    const int q = warp & 3;
+    const int cand_in_tile = q * 32 + lane;
+    uint32_t buf = 0, bphase = 0;
+    for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
+      const int pr = (int)(w % p.npairs);
+      const long st = w / p.npairs;
+      const int tile = (int)(st % p.ntiles), s = (int)(st / p.ntiles);
+      float acc = 0.f;
+      for (int h = 0; h < 2; ++h) {
+        const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
+        if (h == 1 && g == pr) break;
+        mbar_wait(&tfull[buf], bphase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t0 + c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]);
+            acc = fmaf(v, v, acc);
+          }
+          if (p.dbg) {
+            float* o = p.dbg + ((long)s * p.Mc + tile * BM + cand_in_tile) * p.Np + g * BN + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        buf ^= 1;
+        if (buf == 0) bphase ^= 1;
+      }
+      p.partial[((long)pr * p.S + s) * p.ldp + tile * BM + cand_in_tile] = acc;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+__global__ void finish_var_kernel(int M, int c_begin, int Mc, int S, int npairs, int ldp, const float* __restrict__ partial,
+                                  const float* __restrict__ amp2, float* __restrict__ var, int ldm) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (c >= Mc || c_begin + c >= M) return;
+  float t = 0.f;
+  for (int pr = 0; pr < npairs; ++pr) t += partial[((long)pr * S + s) * ldp + c];
+  var[(long)s * ldm + c_begin + c] = amp2[s] * 1.000001f - t;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D row-major float matrix [rows][cols] (cols contiguous), box = (BK cols) x (box_rows rows), 128B swizzle
+static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return 1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+}  // namespace tc
+
+int num_sms();
+
+// ---------------------------------------------------------------------------------------------------- host side
+int tc_np(int N) { return ((N + tc::BN - 1) / tc::BN) * tc::BN; }
+
+size_t trtri_workspace_bytes(int Np, int S) { return (size_t)S * Np * Np * sizeof(float); }
+
+int trtri_split(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi, float* linv_lo,
+                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (Npad <= 0 || Npad % kNpadMult) return -1;
+  if (Np < Npad || Np % tc::BN) return -2;
+  if (S <= 0) return -3;
+  if (!L || !winv || !linv_hi || !linv_lo) return -4;
+  if (!workspace || workspace_bytes < trtri_workspace_bytes(Np, S)) return -8;
+  float* X = reinterpret_cast<float*>(workspace);
+  const size_t dsm = sizeof(TileSmem<float>) + sizeof(float) * 128 * (128 + kPad);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    attr = true;
+  }
+  trtri_kernel<<<dim3(Npad / 128, S), 256, dsm, st>>>(Npad, Np, L, winv, X);
+  const long total = (long)S * Np * Np;
+  split_lower_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Npad, Np, total, X, linv_hi, linv_lo);
+  count_launch(2);
+  return check_launch("trtri_split");
+}
+
+// workspace: Kxt hi | Kxt lo | partial
+static size_t tc_chunk_cands(int Np, int M, int S, size_t budget) {
+  size_t per_cand = 2 * (size_t)S * Np * sizeof(float);
+  size_t mc = budget / per_cand;
+  size_t mpad = ((size_t)M + 127) / 128 * 128;
+  if (mc > mpad) mc = mpad;
+  mc = mc / 128 * 128;
+  if (mc < 128) mc = 128;
+  return mc;
+}
+static const size_t kTcBudget = (size_t)20 << 30;
+
+size_t predict_tc_workspace_bytes(int Np, int M, int S) {
+  size_t mc = tc_chunk_cands(Np, M, S, kTcBudget);
+  int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
+  return 2 * (size_t)S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) + 1024;
+}
+
+int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
+               const float* amp2, const float* mean, const float* linv_hi, const float* linv_lo, const float* alpha,
+               int Npad_alpha, float* mu, float* var, int ldm, void* workspace, size_t workspace_bytes, float* dbg,
+               cudaStream_t st) {
+  if (kind < 0 || kind > 3) return -1;
+  if (N <= 0) return -2;
+  if (Np < N || Np % tc::BN) return -3;
+  if (M <= 0) return -4;
+  if (D <= 0) return -5;
+  if (S <= 0) return -6;
+  if (!X || !Cc || !inv_ls || !amp2 || !mean || !linv_hi || !linv_lo || !alpha || !mu || !var) return -7;
+  if (ldm < M) return -18;
+  if (!workspace || workspace_bytes < predict_tc_workspace_bytes(Np, M, S)) return -19;
+  const int Mc = (int)tc_chunk_cands(Np, M, S, kTcBudget);
+  const int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
+  float* khi = reinterpret_cast<float*>(workspace);
+  float* klo = khi + (size_t)S * Mc * Np;
+  float* partial = klo + (size_t)S * Mc * Np;
+
+  CUtensorMap mAhi, mAlo, mBhi, mBlo;
+  if (tc::make_map(&mAhi, khi, (uint64_t)S * Mc, Np, tc::BM) || tc::make_map(&mAlo, klo, (uint64_t)S * Mc, Np, tc::BM) ||
+      tc::make_map(&mBhi, linv_hi, (uint64_t)S * Np, Np, tc::BN) ||
+      tc::make_map(&mBlo, linv_lo, (uint64_t)S * Np, Np, tc::BN))
+    return 1999;   // SMK_ERR_CUDA range: cuTensorMapEncodeTiled unavailable / failed
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc::predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    attr = true;
+  }
+  const size_t kx_smem = sizeof(float) * (64 * (size_t)(D + 1) + D);
+  static size_t kx_attr = 48 * 1024;
+  if (kx_smem > kx_attr) {
+    cudaFuncSetAttribute(kxt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kx_smem);
+    kx_attr = kx_smem;
+  }
+  for (int c_begin = 0; c_begin < M; c_begin += Mc) {
+    const int mc_used = min(Mc, ((M - c_begin) + 127) / 128 * 128);
+    kxt_kernel<<<dim3(mc_used / 32, S), 256, kx_smem, st>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
+                                                            alpha, Npad_alpha, khi, klo, mu, ldm);
+    tc::Args a;
+    a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
+    a.partial = partial; a.dbg = dbg;
+    long nitems = (long)S * a.ntiles * npairs;
+    int grid = (int)std::min<long>(nitems, num_sms());
+    tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, a);
+    tc::finish_var_kernel<<<dim3((mc_used + 255) / 256, S), 256, 0, st>>>(M, c_begin, mc_used, S, npairs, Mc, partial,
+                                                                        amp2, var, ldm);
+    count_launch(3);
+  }
+  return check_launch("predict_tc");
+}
+
+}  // namespace smk

@@ -18,6 +18,7 @@ HBM layout (T = float32 on the grid path, float64 for log-likelihoods / refineme
 torch provides the allocator and the stream only.  Nothing here falls back to the CPU.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.stats as sps
@@ -73,6 +74,21 @@ class Factor(object):
         check(fn("smk_potrf_lower_batched", dt)(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info), st),
               "potrf")
 
+    def linv(self):
+        """(hi, lo, Np): explicit inverse of the factor split for the 3xTF32 tensor-core predict; computed once."""
+        if getattr(self, "_linv", None) is None:
+            eng, L = self.eng, _lib.lib()
+            S = self.hb.S
+            Np = L.smk_tc_np(self.N)
+            hi = torch.empty((S, Np, Np), dtype=torch.float32, device=eng.device)
+            lo = torch.empty((S, Np, Np), dtype=torch.float32, device=eng.device)
+            nb = L.smk_trtri_workspace_bytes(Np, S)
+            ws = torch.empty((nb,), dtype=torch.uint8, device=eng.device)
+            check(L.smk_trtri_split_f32(self.Npad, Np, S, ptr(self.L), ptr(self.winv), ptr(hi), ptr(lo), ptr(ws), nb,
+                                        eng.stream()), "trtri_split")
+            self._linv = (hi, lo, Np)
+        return self._linv
+
     def check_pd(self):
         """The reference lets spla.cholesky raise LinAlgError (SURVEY 8b 'Errors'); so do we."""
         info = self.info.cpu().numpy()
@@ -125,6 +141,11 @@ class GPEIEngine(object):
         self.esize = 8 if dtype == torch.float64 else 4
         self.NB = _lib.lib().smk_block(self.esize)
         self._ws = None
+        self._ws_tc = None
+        # fused-predict implementation: "tc" = tcgen05/TMEM/TMA 3xTF32 kernel (float32 only), "simt" = register-tiled FMA
+        self.predict_impl = os.environ.get("SMK_PREDICT_IMPL", "tc" if dtype == torch.float32 else "simt")
+        if dtype != torch.float32:
+            self.predict_impl = "simt"
         self.last = {}
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
 
@@ -190,13 +211,25 @@ class GPEIEngine(object):
                                           ptr(hb.amp2), None, ptr(out), M, self.stream()), "cov_build")
         return out
 
-    def predict(self, kind, fac, C_dev, alpha):
+    def predict(self, kind, fac, C_dev, alpha, impl=None, dbg_beta=None):
         """Predictive mean / variance at the candidates for every sample of the factor batch."""
         hb, dt = fac.hb, self.dtype
         M = C_dev.shape[0]
         ldm = _ceil(M, 128)
         mu = torch.empty((hb.S, ldm), dtype=dt, device=self.device)
         var = torch.empty((hb.S, ldm), dtype=dt, device=self.device)
+        if (impl or self.predict_impl) == "tc" and isinstance(fac, Factor):
+            L = _lib.lib()
+            hi, lo, Np = fac.linv()
+            nb = L.smk_predict_tc_workspace_bytes(Np, M, hb.S)
+            if self._ws_tc is None or self._ws_tc.numel() < nb:
+                self._ws_tc = None
+                self._ws_tc = torch.empty((nb,), dtype=torch.uint8, device=self.device)
+            check(L.smk_predict_tc_f32(KINDS[kind], fac.N, Np, M, fac.D, hb.S, ptr(fac.X), ptr(C_dev), ptr(hb.inv_ls),
+                                       ptr(hb.amp2), ptr(hb.mean), ptr(hi), ptr(lo), ptr(alpha), fac.Npad, ptr(mu),
+                                       ptr(var), ldm, ptr(self._ws_tc), nb, ptr(dbg_beta), self.stream()),
+                  "predict_tc")
+            return mu, var, ldm
         nb = _lib.lib().smk_predict_workspace_bytes(self.esize, fac.Npad)
         ws = self.workspace(nb)
         check(fn("smk_predict", dt)(KINDS[kind], fac.N, fac.Npad, M, fac.D, hb.S, ptr(fac.X), ptr(C_dev),

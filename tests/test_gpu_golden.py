@@ -36,12 +36,20 @@ def _check(ei, ref, prec):
 
 
 @pytest.mark.parametrize("name", OPT_CASES)
-@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("prec", ["f64", "f32", "f32-simt"])
 def test_ei_over_hypers_vs_reference(engines, name, prec):
+    """f32 = production path (tcgen05 3xTF32 predict); f32-simt = the register-tiled FMA predict; f64 = logic check."""
     g = load(name)
     comp, pend, cand, vals = sets(g)
-    ei = engines[prec].ei_over_hypers(str(g["kind"]), hypers(g), comp, pend, cand, vals, g["normals"])
-    _check(ei, g["overall_ei"], prec)
+    eng = engines[prec.split("-")[0]]
+    saved = eng.predict_impl
+    if prec == "f32-simt":
+        eng.predict_impl = "simt"
+    try:
+        ei = eng.ei_over_hypers(str(g["kind"]), hypers(g), comp, pend, cand, vals, g["normals"])
+    finally:
+        eng.predict_impl = saved
+    _check(ei, g["overall_ei"], prec.split("-")[0])
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])

@@ -190,3 +190,40 @@ def test_topk_matches_numpy(engines, M, k):
     order = np.lexsort((-np.arange(M), score))       # ascending score, ties: higher index first
     np.testing.assert_array_equal(idx, order[-k:])
     np.testing.assert_array_equal(val, score[idx])
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core predict
+@pytest.mark.parametrize("D,N,M", [(6, 100, 128), (8, 300, 1000), (3, 520, 257)])
+def test_predict_tc_beta_and_moments(engines, D, N, M):
+    """tcgen05 3xTF32 path: the dumped beta^T = Kx^T L^-T tile product (descriptor / swizzle / pipeline check) and
+    the resulting moments, against the oracle."""
+    import torch
+    from spearmint_b200 import _lib
+    eng = engines["f32"]
+    X, Cd, y, hs = _problem(D, N, M, 2, 11)
+    hb = eng.hypers(hs, "Matern52")
+    fac = eng.factor("Matern52", eng.to_dev(X), hb)
+    fac.check_pd()
+    alpha, _, _ = fac.solve(eng.to_dev(y), F=1)
+    hi, lo, Np = fac.linv()
+    Mc = ((M + 127) // 128) * 128
+    dbg = torch.zeros((hb.S, Mc, Np), dtype=torch.float32, device=eng.device)
+    mu, var, ldm = eng.predict("Matern52", fac, eng.to_dev(Cd), alpha.view(hb.S, fac.Npad), impl="tc", dbg_beta=dbg)
+    mu2, var2, _ = eng.predict("Matern52", fac, eng.to_dev(Cd), alpha.view(hb.S, fac.Npad), impl="simt")
+    linv = (hi.double() + lo.double()).cpu().numpy()
+    dbg, mu, var = dbg.double().cpu().numpy(), mu.double().cpu().numpy(), var.double().cpu().numpy()
+    for s, h in enumerate(hs):
+        m_ref, v_ref, L, _ = O.predict("Matern52", h, X, Cd, y)
+        Linv_ref = spla.solve_triangular(L, np.eye(N), lower=True)
+        assert np.abs(linv[s, :N, :N] - Linv_ref).max() <= 2e-3 * np.abs(Linv_ref).max()
+        assert np.all(np.triu(linv[s], 1) == 0)
+        beta_ref = spla.solve_triangular(L, O.cov("Matern52", h[2], h[3], X, Cd), lower=True)      # (N, M)
+        got = dbg[s, :M, :N].T
+        assert np.abs(got - beta_ref).max() <= 2e-3 * np.abs(beta_ref).max(), np.abs(got - beta_ref).max()
+        assert np.all(dbg[s, :M, N:] == 0)
+        floor = 1e-3 if D <= 3 else 2e-4      # eps_fp32 * sum|Kx alpha|: low-D / large-N problems are worse conditioned
+        np.testing.assert_allclose(mu[s, :M], m_ref, rtol=1e-4, atol=floor)
+        np.testing.assert_allclose(var[s, :M], v_ref, rtol=1e-3, atol=floor * h[2])
+    # and against the SIMT kernel of the same library
+    np.testing.assert_allclose(var[:, :M], var2.double().cpu().numpy()[:, :M], rtol=1e-3, atol=floor)
+    np.testing.assert_allclose(mu[:, :M], mu2.double().cpu().numpy()[:, :M], rtol=1e-4, atol=floor)
