@@ -45,6 +45,10 @@ int smk_npad(int N);                       /* N rounded up to the factor block s
 int smk_block(int elem_bytes);             /* diagonal-block size NB: 128 for f32, 64 for f64 */
 long long smk_launch_count(void);          /* kernels launched by this library so far        */
 const char* smk_last_error(void);          /* text of the last SMK_ERR_CUDA                  */
+/* measurement aid: when enabled, CUDA events are recorded on the launch stream around the heavy kernels
+ * ("predict_tc_kernel", "kxt_kernel", "trtri", "predict_kernel"); smk_timing_ms sums spans by name substring. */
+void smk_timing_enable(int on);
+double smk_timing_ms(const char* name_substr, int* count);
 
 /* ---- (1) covariance build: gp.dist2 + kernel + chooser.cov  (GP:34-54, GP:87-127, OPT:207-212)
  * out[s][i][j] = amp2[s] * k_kind((X[i]-Y[j]) * inv_ls[s])  (+ diag below when Y == NULL)

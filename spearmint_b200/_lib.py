@@ -46,6 +46,8 @@ SIGNATURES = {
     "smk_block": ([_i], _i),
     "smk_launch_count": ([], _ll),
     "smk_last_error": ([], C.c_char_p),
+    "smk_timing_enable": ([_i], None),
+    "smk_timing_ms": ([C.c_char_p, _p], C.c_double),
     "smk_predict_workspace_bytes": ([_i, _i], _sz),
     "smk_topk_workspace_bytes": ([_i, _i], _sz),
     "smk_ei_over_hypers_host_f32": ([_i, _i, _i, _i, _i] + [_p] * 9, _i),

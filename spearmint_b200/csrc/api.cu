@@ -15,6 +15,26 @@ static char g_err[512] = "";
 
 void count_launch(int n) { g_launches += n; }
 
+// ---- optional kernel timing: (name, start, stop) event triples recorded around selected launches
+struct TimedSpan { const char* name; cudaEvent_t e0, e1; };
+static std::vector<TimedSpan> g_spans;
+static int g_timing = 0;
+static cudaEvent_t g_open = nullptr;
+
+void timing_begin(const char* name, cudaStream_t st) {
+  if (!g_timing) return;
+  TimedSpan t;
+  t.name = name;
+  cudaEventCreate(&t.e0);
+  cudaEventCreate(&t.e1);
+  cudaEventRecord(t.e0, st);
+  g_spans.push_back(t);
+}
+void timing_end(cudaStream_t st) {
+  if (!g_timing || g_spans.empty()) return;
+  cudaEventRecord(g_spans.back().e1, st);
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) return SMK_OK;
@@ -63,6 +83,26 @@ int smk_npad(int N) { return ((N + kNpadMult - 1) / kNpadMult) * kNpadMult; }
 int smk_block(int elem_bytes) { return elem_bytes == 8 ? Cfg<double>::NB : Cfg<float>::NB; }
 long long smk_launch_count(void) { return g_launches.load(); }
 const char* smk_last_error(void) { return g_err; }
+
+void smk_timing_enable(int on) {
+  g_timing = on;
+  for (auto& t : g_spans) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  g_spans.clear();
+}
+/* Sum of the recorded durations (ms) of every span whose name contains `substr`, and their count.
+ * Synchronises on the recorded events; spans stay recorded until smk_timing_enable() is called again. */
+double smk_timing_ms(const char* substr, int* count) {
+  double tot = 0.0;
+  int n = 0;
+  for (auto& t : g_spans) {
+    if (substr && !strstr(t.name, substr)) continue;
+    cudaEventSynchronize(t.e1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) { tot += ms; ++n; }
+  }
+  if (count) *count = n;
+  return tot;
+}
 
 int smk_cov_build_f32(int kind, int N, int M, int D, int S, const float* X, const float* Y, const float* inv_ls,
                       const float* amp2, const float* diag_add, float* out, int ld, void* stream) {

@@ -239,7 +239,9 @@ int predict(int kind, int N, int Npad, int M, int D, int S, const T* X, const T*
   a.kind = kind; a.N = N; a.Npad = Npad; a.M = M; a.D = D; a.S = S; a.ldm = ldm; a.ntiles = ntiles;
   a.X = X; a.C = Cc; a.inv_ls = inv_ls; a.amp2 = amp2; a.mean = mean; a.L = L; a.winv = winv; a.alpha = alpha;
   a.mu = mu; a.var = var; a.scratch = reinterpret_cast<T*>(workspace);
+  timing_begin("predict_kernel", st);
   predict_kernel<T><<<grid, 256, dsm, st>>>(a);
+  timing_end(st);
   count_launch();
   return check_launch("predict");
 }

@@ -103,63 +103,102 @@ __global__ void split_lower_kernel(int Npad, int ld, long total, const float* __
 }
 
 // ================================================================================================= kxt (SIMT)
-// One block = 32 candidates x all n (tiles of 32): Kxt[s][c][n] (hi, lo), mu[s][c].  grid = (Mc/32, S).
-__global__ void __launch_bounds__(256) kxt_kernel(int kind, int N, int Np, int M, int c_begin, int Mc, int D,
-                                                  const float* __restrict__ X, const float* __restrict__ Cc,
-                                                  const float* __restrict__ inv_ls, const float* __restrict__ amp2,
-                                                  const float* __restrict__ mean, const float* __restrict__ alpha,
-                                                  int Npad_alpha, float* __restrict__ khi, float* __restrict__ klo,
-                                                  float* __restrict__ mu, int ldm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* cs = reinterpret_cast<float*>(smem_raw);   // [32][D+1] scaled candidates
-  float* xs = cs + 32 * (D + 1);                    // [32][D+1] scaled X tile
-  float* il = xs + 32 * (D + 1);                    // [D]
-  const int s = blockIdx.y, c0 = blockIdx.x * 32;   // c0 relative to the chunk
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int d = threadIdx.x; d < D; d += 256) il[d] = inv_ls[(long)s * D + d];
-  __syncthreads();
-  for (int e = threadIdx.x; e < 32 * D; e += 256) {
-    int c = e / D, d = e % D;
-    int gc = min(c_begin + c0 + c, M - 1);
-    cs[c * (D + 1) + d] = Cc[(long)gc * D + d] * il[d];
-  }
+// One block = 128 candidates x all n in tiles of 128, 8x8 register micro-tiles (rows = candidates, cols = n):
+// Kxt[s][c][n] as (hi, lo) float4 stores (256 B contiguous per 16 threads), mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.
+// grid = (Mc/128, S).  Output-bound: 8 B written per (3D + 25) flops.
+constexpr int kKD = 32;   // D chunk staged in shared memory
+
+__global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, int M, int c_begin, int Mc, int D,
+                                                     const float* __restrict__ X, const float* __restrict__ Cc,
+                                                     const float* __restrict__ inv_ls, const float* __restrict__ amp2,
+                                                     const float* __restrict__ mean, const float* __restrict__ alpha,
+                                                     int Npad_alpha, float* __restrict__ khi, float* __restrict__ klo,
+                                                     float* __restrict__ mu, int ldm) {
+  constexpr int T = 128, LDT = T + kPad;
+  __shared__ __align__(16) float cs[kKD][LDT];    // scaled candidates   [d][cand]
+  __shared__ __align__(16) float xs[kKD][LDT];    // scaled observations [d][n]
+  __shared__ float red[16][T];
+  const int s = blockIdx.y, c0 = blockIdx.x * T;  // c0 relative to the chunk
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const float* ils = inv_ls + (long)s * D;
   const float a2 = amp2[s];
   const float* al = alpha + (long)s * Npad_alpha;
-  float macc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int n0 = 0; n0 < Np; n0 += 32) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < 32 * D; e += 256) {
-      int i = e / D, d = e % D, n = n0 + i;
-      xs[i * (D + 1) + d] = (n < N) ? X[(long)n * D + d] * il[d] : 0.f;
-    }
-    __syncthreads();
-    const int n = n0 + tx;
-    const float an = (n < N) ? al[n] : 0.f;
-    const float* xr = xs + tx * (D + 1);
+  float mdot[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = ty + 8 * k;
-      const float* cr = cs + c * (D + 1);
-      float r2 = 0.f;
-      for (int d = 0; d < D; ++d) {
-        float df = xr[d] - cr[d];
-        r2 = fmaf(df, df, r2);
+  for (int r = 0; r < 8; ++r) mdot[r] = 0.f;
+
+  for (int n0 = 0; n0 < Np; n0 += T) {
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += kKD) {
+      __syncthreads();
+      for (int e = tid; e < T * kKD; e += 256) {
+        int row = e / kKD, dd = e % kKD, d = d0 + dd;
+        int gc = min(c_begin + c0 + row, M - 1), n = n0 + row;
+        float sc = (d < D) ? ils[d] : 0.f;
+        cs[dd][row] = (d < D) ? Cc[(long)gc * D + d] * sc : 0.f;
+        xs[dd][row] = (d < D && n < N) ? X[(long)n * D + d] * sc : 0.f;
       }
-      float kv = (n < N) ? a2 * kernel_of_r2<float>(kind, r2) : 0.f;
-      macc[k] = fmaf(an, kv, macc[k]);
-      float h = tf32_hi(kv);
-      long o = ((long)s * Mc + c0 + c) * Np + n;
-      khi[o] = h;
-      klo[o] = kv - h;
+      __syncthreads();
+      const int dmax = min(kKD, D - d0);
+      for (int dd = 0; dd < dmax; ++dd) {
+        float a[8], b[8];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          V4<float> t = ld4(&cs[dd][g * 64 + ty * 4]);
+          V4<float> u = ld4(&xs[dd][g * 64 + tx * 4]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { a[g * 4 + e] = t.v[e]; b[g * 4 + e] = u.v[e]; }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float df = a[r] - b[c];
+            acc[r][c] = fmaf(df, df, acc[r][c]);
+          }
+      }
+    }
+    float av[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      int n = n0 + tile_col(tx, c);
+      av[c] = (n < N) ? al[n] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float* oh = khi + ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
+      float* ol = klo + ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        V4<float> h, l;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = g * 4 + e;
+          const int n = n0 + g * 64 + tx * 4 + e;
+          float kv = (n < N) ? a2 * kernel_of_r2<float>(kind, acc[r][c]) : 0.f;
+          mdot[r] = fmaf(av[c], kv, mdot[r]);
+          h.v[e] = tf32_hi(kv);
+          l.v[e] = kv - h.v[e];
+        }
+        st4(oh + g * 64 + tx * 4, h);
+        st4(ol + g * 64 + tx * 4, l);
+      }
     }
   }
+  // mean: reduce the per-thread row partials over the 16 column-threads (fixed order -> deterministic)
+  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float v = macc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    int gc = c_begin + c0 + ty + 8 * k;
-    if (tx == 0 && gc < M) mu[(long)s * ldm + gc] = v + mean[s];
+  for (int r = 0; r < 8; ++r) red[tx][tile_row(ty, r)] = mdot[r];
+  __syncthreads();
+  if (tid < T) {
+    float v = 0.f;
+    for (int q = 0; q < 16; ++q) v += red[q][tid];
+    int gc = c_begin + c0 + tid;
+    if (gc < M) mu[(long)s * ldm + gc] = v + mean[s];
   }
 }
 
@@ -167,9 +206,11 @@ __global__ void __launch_bounds__(256) kxt_kernel(int kind, int N, int Np, int M
 namespace tc {
 constexpr int BM = 128;        // candidates per tile (TMEM lanes, MMA M)
 constexpr int BN = 256;        // rows of Linv per group (MMA N, TMEM columns per accumulator)
-constexpr int BK = 32;         // k per stage: 32 x 4 B = one 128-byte swizzle row
+constexpr int BK = 16;         // k per stage: 16 x 4 B = one 64-byte swizzle row (BK = 32 -> 128-byte swizzle)
 constexpr int UK = 8;          // k per tcgen05.mma.kind::tf32
-constexpr int STAGES = 2;
+constexpr int STAGES = 4;      // 4 x 48 KB: a TMA refill (~1.3 us from HBM) hides behind 3 stages of MMA (3 x 0.45 us)
+constexpr int ROW_BYTES = BK * 4;                  // swizzle span = operand row in shared memory
+static_assert(ROW_BYTES == 64 || ROW_BYTES == 128, "operand rows must be one 64B or 128B swizzle span");
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 constexpr int B_BYTES = BN * BK * 4;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
@@ -206,14 +247,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), LBO unused (=1).
+// K-major swizzled operand tile: rows of ROW_BYTES, 8-row swizzle atoms (SBO = 8 rows), LBO unused (=1).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;             // stride byte offset: 8 rows
+  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;         // SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return d;
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
@@ -415,7 +456,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D row-major float matrix [rows][cols] (cols contiguous), box = (BK cols) x (box_rows rows), 128B swizzle
+// 2-D row-major float matrix [rows][cols] (cols contiguous), box = (BK cols) x (box_rows rows), swizzle = row bytes
 static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn f = encode_fn();
   if (!f) return 1;
@@ -424,7 +465,9 @@ static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t co
   cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
@@ -451,7 +494,9 @@ int trtri_split(int Npad, int Np, int S, const float* L, const float* winv, floa
     cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
     attr = true;
   }
+  timing_begin("trtri_kernel", st);
   trtri_kernel<<<dim3(Npad / 128, S), 256, dsm, st>>>(Npad, Np, L, winv, X);
+  timing_end(st);
   const long total = (long)S * Np * Np;
   split_lower_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Npad, Np, total, X, linv_hi, linv_lo);
   count_launch(2);
@@ -505,22 +550,20 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     cudaFuncSetAttribute(tc::predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     attr = true;
   }
-  const size_t kx_smem = sizeof(float) * (64 * (size_t)(D + 1) + D);
-  static size_t kx_attr = 48 * 1024;
-  if (kx_smem > kx_attr) {
-    cudaFuncSetAttribute(kxt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kx_smem);
-    kx_attr = kx_smem;
-  }
   for (int c_begin = 0; c_begin < M; c_begin += Mc) {
     const int mc_used = min(Mc, ((M - c_begin) + 127) / 128 * 128);
-    kxt_kernel<<<dim3(mc_used / 32, S), 256, kx_smem, st>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
-                                                            alpha, Npad_alpha, khi, klo, mu, ldm);
+    timing_begin("kxt_kernel", st);
+    kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, st>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
+                                                       alpha, Npad_alpha, khi, klo, mu, ldm);
+    timing_end(st);
     tc::Args a;
     a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
     a.partial = partial; a.dbg = dbg;
     long nitems = (long)S * a.ntiles * npairs;
     int grid = (int)std::min<long>(nitems, num_sms());
+    timing_begin("predict_tc_kernel", st);
     tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, a);
+    timing_end(st);
     tc::finish_var_kernel<<<dim3((mc_used + 255) / 256, S), 256, 0, st>>>(M, c_begin, mc_used, S, npairs, Mc, partial,
                                                                         amp2, var, ldm);
     count_launch(3);
