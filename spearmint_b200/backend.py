@@ -54,7 +54,10 @@ class DeviceBackend(object):
         st.hs = [hyper_samples[s] for s in mine]
         st.ths = None if time_hyper_samples is None else [time_hyper_samples[s] for s in mine]
         P = 0 if pend is None else pend.shape[0]
-        F = 1 if P == 0 else normals.shape[1]
+        F = 1 if P == 0 else normals.shape[-1]
+        if normals is not None and np.ndim(normals) == 3:      # per-sample normals follow their samples to the owning rank
+            normals = normals[mine]
+            st.args = (comp, pend, vals, normals, durs_log)
         chunk = eng.max_samples_per_chunk(_ceil(comp.shape[0] + P, 128), _ceil(200000, 128), F)
         st.preps = None
         if st.hs and len(st.hs) <= chunk:            # everything resident: prepare once, sweep many

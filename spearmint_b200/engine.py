@@ -309,8 +309,9 @@ class GPEIEngine(object):
         The joint (N+P) factor and all big solves run on the device; the P x P conditional of the pending points
         (P <= max_concurrent, a handful) and the fantasy draw use the host in float64 with the caller's normals, so
         the host RNG order is the reference's."""
-        N, P, F = Xo.shape[0], Pd.shape[0], normals.shape[1]
+        N, P, F = Xo.shape[0], Pd.shape[0], normals.shape[-1]
         S = hb.S
+        per_sample = (normals.ndim == 3)     # (S,P,F): GPEIChooser draws fresh normals per hyper-sample (GPEI:237)
         Xj = torch.cat([Xo, Pd], dim=0).contiguous()
         fac = self.factor(kind, Xj, hb)
         fac.check_pd()
@@ -327,7 +328,7 @@ class GPEIEngine(object):
             Lp = np.tril(Lpp[s])
             pend_K = Lp.dot(Lp.T) - hb.host_noise[s] * np.eye(P)
             pend_chol = np.linalg.cholesky(pend_K)                                # LinAlgError like OPT:585
-            pf = pend_chol.dot(normals) + pend_m[s][:, None]                      # (P,F)  OPT:589
+            pf = pend_chol.dot(normals[s] if per_sample else normals) + pend_m[s][:, None]   # (P,F)  OPT:589
             fant[s, :, :N] = vals[None, :]
             fant[s, :, N:] = pf.T
             bests[s] = np.minimum(vals.min(), pf.min(axis=0))                     # OPT:597
@@ -373,13 +374,14 @@ class GPEIEngine(object):
         N = res["X"].shape[0] if res is not None else comp.shape[0]
         M = Cd.shape[0]
         ldm = _ceil(M, 128)
-        Fn = 1 if P == 0 else int(normals.shape[1])
+        Fn = 1 if P == 0 else int(normals.shape[-1])
         chunk = self.max_samples_per_chunk(_ceil(N + P, 128), ldm, Fn)
         ei_sum = torch.zeros((ldm,), dtype=self.dtype, device=self.device)
         ei_all = torch.empty((S, ldm), dtype=self.dtype, device=self.device) if want_matrix else None
         for s0 in range(0, S, chunk):
             r = res if (res is not None and chunk >= S) else (dict(res, hb=None) if res is not None else None)
-            prep = self.prepare(kind, hyper_samples[s0:s0 + chunk], comp, pend, vals, normals,
+            nrm = normals[s0:s0 + chunk] if (normals is not None and np.ndim(normals) == 3) else normals
+            prep = self.prepare(kind, hyper_samples[s0:s0 + chunk], comp, pend, vals, nrm,
                                 None if time_hyper_samples is None else time_hyper_samples[s0:s0 + chunk],
                                 durs_log, resident=r)
             ei, _ = self.ei_prepared(prep, Cd, want_matrix, ei_sum)

@@ -28,8 +28,13 @@ class OracleBackend(object):
         return st
 
     def ei_matrix(self, st, cand):
-        if st.ths is None:
+        if st.ths is None and (st.normals is None or np.ndim(st.normals) == 2):
             return O.ei_over_hypers(st.kind, st.hs, st.comp, st.pend, cand, st.vals, st.normals)
+        if st.ths is None:      # per-sample fantasy normals (GPEIChooser)
+            out = np.zeros((cand.shape[0], len(st.hs)))
+            for s, h in enumerate(st.hs):
+                out[:, s] = O.compute_ei(st.kind, h, st.comp, st.pend, cand, st.vals, st.normals[s])
+            return out
         out = np.zeros((cand.shape[0], len(st.hs)))
         for s, (h, th) in enumerate(zip(st.hs, st.ths)):
             out[:, s] = O.compute_ei_per_s(st.kind, h, th, st.comp, st.pend, cand, st.vals, st.durs, st.normals)

@@ -137,3 +137,17 @@ def test_per_second_gradient_oracle_matches_reference():
         f, gr = O.grad_optimize_ei_per_s_over_hypers(str(g["kind"]), hs[:S], ths[:S], x, comp, vals, durs)
         np.testing.assert_allclose(f, f_ref, rtol=1e-8)
         np.testing.assert_allclose(gr, g_ref, rtol=1e-7, atol=1e-12)
+
+
+def test_gpei_chooser_next_reproduces_reference(tmp_path):
+    """GPEIChooser (f3): interleaved sample / fantasy-normal RNG order, argmax of the mean EI on the grid."""
+    from spearmint_b200.chooser import GPEIChooserB200 as mod
+    g = load("gpei_d3")
+    ch = mod.init(str(tmp_path), "mcmc_iters=4")
+    ch._backend = OracleBackend()
+    np.random.seed(int(g["seed"]))
+    ret = ch.next(g["grid"], g["values"], g["durations"], g["candidates"], g["pending"], g["complete"])
+    assert isinstance(ret, int) and ret == int(g["next_index"])
+    ch.dump_hypers()
+    st = pickle.load(open(ch.state_pkl, "rb"))
+    assert sorted(st) == ["amp2", "dims", "ls", "mean", "noise"]

@@ -126,3 +126,13 @@ def test_per_second_refine_gradient(backend):
         f, gr = ctx.value_grad(x)
         np.testing.assert_allclose(f, f_ref, rtol=1e-7)
         np.testing.assert_allclose(gr, g_ref, rtol=1e-6, atol=1e-11)
+
+
+def test_gpei_chooser_next_matches_reference(backend, tmp_path):
+    from spearmint_b200.chooser import GPEIChooserB200 as mod
+    g = load("gpei_d3")
+    ch = mod.init(str(tmp_path), "mcmc_iters=4")
+    ch._backend = backend
+    np.random.seed(int(g["seed"]))
+    ret = ch.next(g["grid"], g["values"], g["durations"], g["candidates"], g["pending"], g["complete"])
+    assert ret == int(g["next_index"])
