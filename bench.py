@@ -330,10 +330,34 @@ def run_b200_arm(args, D, N, M, S):
         if cpu is not None:
             out["cpu_baseline"] = {"value": cpu["value"], "unit": "candidates/s", "cores": os.cpu_count(),
                                    "kind": "port", "sample": cpu["sample"]}
+        if world == 1 and not args.no_next:
+            out["next"] = next_wall_ms(args)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def next_wall_ms(args):
+    """Second half of BASELINE.json's metric: chooser.next() wall-ms through the plugin API (MCMC chain with the GPU
+    float64 log-likelihood -> grid pass -> L-BFGS refinement with cached factors -> grid pass).  Measured at the `c2`
+    configuration (D=8, N=512, 10k candidates, 10 hyper-samples, reference defaults burnin=100, grid_subset=20); the CPU
+    figure (same host logic on the oracle numerics = a port of the reference's next()) only with --next-cpu: it takes
+    ~20 s per call."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import next_bench
+    D, N, M, S = WORKLOADS["c2"]
+    calls = next_bench.run("gpu", D, N, M, S, burnin=100, calls=3, grid_subset=20)
+    out = {"workload": "c2 D=%d N=%d M=%d S=%d burnin=100 grid_subset=20" % (D, N, M, S),
+           "ms_first_call_with_burnin": calls[0]["ms"], "ms_steady": float(np.mean([c["ms"] for c in calls[1:]])),
+           "unit": "ms", "refine_evals": calls[-1]["refine_evals"]}
+    if args.next_cpu:
+        cpu = next_bench.run("cpu", D, N, M, S, burnin=100, calls=2, grid_subset=20)
+        out["cpu_port_ms_steady"] = cpu[-1]["ms"]
+        out["cpu_port_ms_first_call"] = cpu[0]["ms"]
+        out["cpu_cores"] = os.cpu_count()
+    return out
 
 
 def main():
@@ -345,6 +369,8 @@ def main():
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-cands", type=int, default=None, help="candidates in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-next", action="store_true", help="skip the chooser.next() wall-ms leg")
+    ap.add_argument("--next-cpu", action="store_true", help="also time the CPU port of next() (slow)")
     args = ap.parse_args()
     D, N, M, S = WORKLOADS[args.workload]
     if args.impl == "reference":

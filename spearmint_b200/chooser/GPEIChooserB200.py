@@ -128,39 +128,40 @@ class GPEIChooserB200(object):
         self._sample_ls(comp, vals)
 
     def _sample_ls(self, comp, vals):
-        def logprob(ls):
-            if np.any(ls < 0) or np.any(ls > self.max_ls):
-                return -np.inf
-            return self._ll(self.mean, self.noise, self.amp2, ls)
-        self.ls = util.slice_sample(self.ls, logprob, compwise=True)
+        mean, noise, amp2, max_ls = self.mean, self.noise, self.amp2, self.max_ls
+
+        def hypers_of(ls):
+            if np.any(ls < 0) or np.any(ls > max_ls):
+                return None
+            return (mean, noise, amp2, ls), ()
+        self.ls = util.slice_sample(self.ls, util.make_logprob(self._ll, hypers_of), compwise=True)
 
     def _sample_noisy(self, comp, vals):
-        vmax, vmin = np.max(vals), np.min(vals)
+        vmax, vmin, ls = np.max(vals), np.min(vals), self.ls
 
-        def logprob(hypers):
+        def hypers_of(hypers):
             mean, amp2, noise = hypers[0], hypers[1], hypers[2]
             if mean > vmax or mean < vmin:
-                return -np.inf
+                return None
             if amp2 < 0 or noise < 0:
-                return -np.inf
-            lp = self._ll(mean, noise, amp2, self.ls)
-            lp += np.log(np.log(1 + (self.noise_scale / noise) ** 2))
-            lp -= 0.5 * (np.log(amp2) / self.amp2_scale) ** 2              # log(amp2): GPEI:312
-            return lp
-        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]), logprob, compwise=False)
+                return None
+            return (mean, noise, amp2, ls), (
+                np.log(np.log(1 + (self.noise_scale / noise) ** 2)),
+                -0.5 * (np.log(amp2) / self.amp2_scale) ** 2)              # log(amp2): GPEI:312
+        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]),
+                                   util.make_logprob(self._ll, hypers_of), compwise=False)
         self.mean, self.amp2, self.noise = hypers[0], hypers[1], hypers[2]
 
     def _sample_noiseless(self, comp, vals):
-        vmax, vmin = np.max(vals), np.min(vals)
+        vmax, vmin, ls = np.max(vals), np.min(vals), self.ls
 
-        def logprob(hypers):
+        def hypers_of(hypers):
             mean, amp2 = hypers[0], hypers[1]
             if mean > vmax or mean < vmin:
-                return -np.inf
+                return None
             if amp2 < 0:
-                return -np.inf
-            lp = self._ll(mean, 1e-3, amp2, self.ls)
-            lp -= 0.5 * (np.log(amp2) / self.amp2_scale) ** 2
-            return lp
-        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]), logprob, compwise=False)
+                return None
+            return (mean, 1e-3, amp2, ls), (-0.5 * (np.log(amp2) / self.amp2_scale) ** 2,)
+        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]),
+                                   util.make_logprob(self._ll, hypers_of), compwise=False)
         self.mean, self.amp2, self.noise = hypers[0], hypers[1], 1e-3

@@ -261,46 +261,43 @@ class GPEIOptChooserB200(object):
         self.hyper_samples.append((self.mean, self.noise, self.amp2, self.ls))
 
     def _sample_ls(self, comp, vals):
-        ll = self._ll(comp, vals)
+        mean, noise, amp2, max_ls = self.mean, self.noise, self.amp2, self.max_ls
 
-        def logprob(ls):
-            if np.any(ls < 0) or np.any(ls > self.max_ls):
-                return -np.inf
-            return ll(self.mean, self.noise, self.amp2, ls)
+        def hypers_of(ls):
+            if np.any(ls < 0) or np.any(ls > max_ls):
+                return None
+            return (mean, noise, amp2, ls), ()
 
-        self.ls = util.slice_sample(self.ls, logprob, compwise=True)
+        self.ls = util.slice_sample(self.ls, util.make_logprob(self._ll(comp, vals), hypers_of), compwise=True)
 
     def _sample_noisy(self, comp, vals):
-        ll = self._ll(comp, vals)
-        vmax, vmin = np.max(vals), np.min(vals)
+        vmax, vmin, ls = np.max(vals), np.min(vals), self.ls
 
-        def logprob(hypers):
+        def hypers_of(hypers):
             mean, amp2, noise = hypers[0], hypers[1], hypers[2]
             if mean > vmax or mean < vmin:
-                return -np.inf
+                return None
             if amp2 < 0 or noise < 0:
-                return -np.inf
-            lp = ll(mean, noise, amp2, self.ls)
-            lp += np.log(np.log(1 + (self.noise_scale / noise) ** 2))        # horseshoe prior on the noise
-            lp -= 0.5 * (np.log(np.sqrt(amp2)) / self.amp2_scale) ** 2       # log-normal prior on the amplitude
-            return lp
+                return None
+            return (mean, noise, amp2, ls), (
+                np.log(np.log(1 + (self.noise_scale / noise) ** 2)),           # horseshoe prior on the noise
+                -0.5 * (np.log(np.sqrt(amp2)) / self.amp2_scale) ** 2)        # log-normal prior on the amplitude
 
-        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]), logprob, compwise=False)
+        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]),
+                                   util.make_logprob(self._ll(comp, vals), hypers_of), compwise=False)
         self.mean, self.amp2, self.noise = hypers[0], hypers[1], hypers[2]
 
     def _sample_noiseless(self, comp, vals):
-        ll = self._ll(comp, vals)
-        vmax, vmin = np.max(vals), np.min(vals)
+        vmax, vmin, ls = np.max(vals), np.min(vals), self.ls
 
-        def logprob(hypers):
+        def hypers_of(hypers):
             mean, amp2 = hypers[0], hypers[1]
             if mean > vmax or mean < vmin:
-                return -np.inf
+                return None
             if amp2 < 0:
-                return -np.inf
-            lp = ll(mean, 1e-3, amp2, self.ls)
-            lp -= 0.5 * (np.log(np.sqrt(amp2)) / self.amp2_scale) ** 2
-            return lp
+                return None
+            return (mean, 1e-3, amp2, ls), (-0.5 * (np.log(np.sqrt(amp2)) / self.amp2_scale) ** 2,)
 
-        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]), logprob, compwise=False)
+        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]),
+                                   util.make_logprob(self._ll(comp, vals), hypers_of), compwise=False)
         self.mean, self.amp2, self.noise = hypers[0], hypers[1], 1e-3

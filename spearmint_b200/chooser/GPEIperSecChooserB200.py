@@ -210,63 +210,65 @@ class GPEIperSecChooserB200(object):
         self.time_hyper_samples.append((self.time_mean, self.time_noise, self.time_amp2, self.time_ls))
 
     def _sample_ls(self, comp, vals):
-        def logprob(ls):
-            if np.any(ls < 0) or np.any(ls > self.max_ls):
-                return -np.inf
-            return self._ll_obj(self.mean, self.noise, self.amp2, ls)
-        self.ls = util.slice_sample(self.ls, logprob, compwise=True)
+        mean, noise, amp2, max_ls = self.mean, self.noise, self.amp2, self.max_ls
+
+        def hypers_of(ls):
+            if np.any(ls < 0) or np.any(ls > max_ls):
+                return None
+            return (mean, noise, amp2, ls), ()
+        self.ls = util.slice_sample(self.ls, util.make_logprob(self._ll_obj, hypers_of), compwise=True)
 
     def _sample_time_ls(self, comp, durs):
-        def logprob(ls):
-            if np.any(ls < 0) or np.any(ls > self.time_max_ls):
-                return -np.inf
-            return self._ll_time(self.time_mean, self.time_noise, self.time_amp2, ls)
-        self.time_ls = util.slice_sample(self.time_ls, logprob, compwise=True)
+        mean, noise, amp2, max_ls = self.time_mean, self.time_noise, self.time_amp2, self.time_max_ls
+
+        def hypers_of(ls):
+            if np.any(ls < 0) or np.any(ls > max_ls):
+                return None
+            return (mean, noise, amp2, ls), ()
+        self.time_ls = util.slice_sample(self.time_ls, util.make_logprob(self._ll_time, hypers_of), compwise=True)
 
     def _sample_noisy(self, comp, vals):
-        vmax, vmin = np.max(vals), np.min(vals)
+        vmax, vmin, ls = np.max(vals), np.min(vals), self.ls
 
-        def logprob(hypers):
+        def hypers_of(hypers):
             mean, amp2, noise = hypers[0], hypers[1], hypers[2]
             if mean > vmax or mean < vmin:
-                return -np.inf
+                return None
             if amp2 < 0 or noise < 0:
-                return -np.inf
-            lp = self._ll_obj(mean, noise, amp2, self.ls)
-            lp += np.log(np.log(1 + (self.noise_scale / noise) ** 2))
-            lp -= 0.5 * (np.log(amp2) / self.amp2_scale) ** 2               # log(amp2), not log(sqrt(amp2)): PSEC:614
-            return lp
-        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]), logprob, compwise=False)
+                return None
+            return (mean, noise, amp2, ls), (
+                np.log(np.log(1 + (self.noise_scale / noise) ** 2)),
+                -0.5 * (np.log(amp2) / self.amp2_scale) ** 2)               # log(amp2), not log(sqrt(amp2)): PSEC:614
+        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]),
+                                   util.make_logprob(self._ll_obj, hypers_of), compwise=False)
         self.mean, self.amp2, self.noise = hypers[0], hypers[1], hypers[2]
 
     def _sample_time_noisy(self, comp, durs):
-        vmax, vmin = np.max(durs), np.min(durs)
+        vmax, vmin, ls = np.max(durs), np.min(durs), self.time_ls
 
-        def logprob(hypers):
+        def hypers_of(hypers):
             mean, amp2, noise = hypers[0], hypers[1], hypers[2]
             if mean > vmax or mean < vmin:
-                return -np.inf
+                return None
             if amp2 < 0 or noise < 0:
-                return -np.inf
-            lp = self._ll_time(mean, noise, amp2, self.time_ls)
-            lp += np.log(np.log(1 + (self.time_noise_scale / noise) ** 2))
-            lp -= 0.5 * (np.log(np.sqrt(amp2)) / self.time_amp2_scale) ** 2   # PSEC:646
-            return lp
-        hypers = util.slice_sample(np.array([self.time_mean, self.time_amp2, self.time_noise]), logprob,
-                                   compwise=False)
+                return None
+            return (mean, noise, amp2, ls), (
+                np.log(np.log(1 + (self.time_noise_scale / noise) ** 2)),
+                -0.5 * (np.log(np.sqrt(amp2)) / self.time_amp2_scale) ** 2)   # PSEC:646
+        hypers = util.slice_sample(np.array([self.time_mean, self.time_amp2, self.time_noise]),
+                                   util.make_logprob(self._ll_time, hypers_of), compwise=False)
         self.time_mean, self.time_amp2, self.time_noise = hypers[0], hypers[1], hypers[2]
 
     def _sample_noiseless(self, comp, vals):
-        vmax, vmin = np.max(vals), np.min(vals)
+        vmax, vmin, ls = np.max(vals), np.min(vals), self.ls
 
-        def logprob(hypers):
+        def hypers_of(hypers):
             mean, amp2 = hypers[0], hypers[1]
             if mean > vmax or mean < vmin:
-                return -np.inf
+                return None
             if amp2 < 0:
-                return -np.inf
-            lp = self._ll_obj(mean, 1e-3, amp2, self.ls)
-            lp -= 0.5 * (np.log(amp2) / self.amp2_scale) ** 2
-            return lp
-        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]), logprob, compwise=False)
+                return None
+            return (mean, 1e-3, amp2, ls), (-0.5 * (np.log(amp2) / self.amp2_scale) ** 2,)
+        hypers = util.slice_sample(np.array([self.mean, self.amp2, self.noise]),
+                                   util.make_logprob(self._ll_obj, hypers_of), compwise=False)
         self.mean, self.amp2, self.noise = hypers[0], hypers[1], 1e-3

@@ -12,15 +12,56 @@
 namespace smk {
 
 // ------------------------------------------------------------------------------------------ diag
+// Factor one NB x NB diagonal block and invert its factor, entirely on one SM (this kernel is the serial spine of
+// the factorisation: nblk launches per matrix, so its latency -- not its flops -- is what matters, above all for
+// the one-matrix-at-a-time log-likelihood calls of the slice sampler).
+//   for each 32-wide sub-block:  (a) warp 0 factors the 32 x 32 diagonal piece AND inverts it in registers with
+//   warp shuffles (no block barriers);  (b) rows below: X = A_sub * Wdd^T;  (c) rank-32 update of what is left.
+//   Then W = L^-1 is assembled from the 32 x 32 inverses by block distance (d = 1, 2, ...).
+template <typename T>
+__device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// lane i holds row i of a 32x32 SPD block (lower part used) in r[0..31]; on exit r = row i of L, w = COLUMN `lane` of L^-1
+template <typename T>
+__device__ __forceinline__ void warp_chol_inv_32(T (&r)[32], T (&w)[32], int lane, int& bad) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    T d = shfl_t(r[j], j);
+    if (!(d > T(0))) { if (bad < 0) bad = j; d = T(1); }
+    const T piv = smk_sqrt(d), ipiv = T(1) / piv;
+    if (lane == j) r[j] = piv;
+    else if (lane > j) r[j] *= ipiv;
+#pragma unroll
+    for (int k = j + 1; k < 32; ++k) {
+      T lkj = shfl_t(r[j], k);
+      if (lane >= k) r[k] = fma(-r[j], lkj, r[k]);
+    }
+  }
+  // forward substitution for column `lane` of the inverse: w_i = (delta - sum_{k<i} L_ik w_k) / L_ii
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    T acc = (i == lane) ? T(1) : T(0);
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      T lik = shfl_t(r[k], i);              // L[i][k], uniform over the warp
+      acc = fma(-lik, w[k], acc);           // w[k] is 0 for k < lane
+    }
+    T lii = shfl_t(r[i], i);
+    w[i] = (i >= lane) ? acc / lii : T(0);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) potrf_diag_kernel(int Npad, int jb, T* __restrict__ A,
                                                           T* __restrict__ winv, int* __restrict__ info) {
-  constexpr int NB = Cfg<T>::NB;
+  constexpr int NB = Cfg<T>::NB, SB = 32, NSB = NB / SB;
   constexpr int LDS = NB + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* a = reinterpret_cast<T*>(smem_raw);   // [NB][LDS] block being factored
-  T* w = a + NB * LDS;                     // [NB][LDS] its inverse
-  const int s = blockIdx.x, tid = threadIdx.x;
+  T* a = reinterpret_cast<T*>(smem_raw);   // [NB][LDS] block being factored (lower)
+  T* w = a + NB * LDS;                     // [NB][LDS] its inverse (lower)
+  T* t = w + NB * LDS;                     // [NB][SB+1] scratch for the panel / inverse assembly
+  constexpr int LDT = SB + 1;
+  const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   T* Ab = A + (long)s * Npad * Npad + (long)jb * NB * Npad + (long)jb * NB;
 
   for (int e = tid; e < NB * NB; e += 256) {
@@ -30,38 +71,82 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(int Npad, int jb, T* __
   }
   __syncthreads();
 
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < NB; ++j) {
-    if (tid == 0) {
-      T d = a[j * LDS + j];
-      if (!(d > T(0))) {               // also catches NaN
-        if (info[s] == 0) info[s] = jb * NB + j + 1;
-        d = T(1);
+  for (int sb = 0; sb < NSB; ++sb) {
+    const int o = sb * SB;
+    // (a) 32x32 diagonal piece: factor + invert in registers of warp 0
+    if (warp == 0) {
+      T r[32], wc[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) r[k] = a[(o + lane) * LDS + o + k];
+      int bad = -1;
+      warp_chol_inv_32<T>(r, wc, lane, bad);
+      bad = __reduce_max_sync(0xffffffffu, bad);     // identical on all lanes anyway
+      if (bad >= 0 && lane == 0 && info[s] == 0) info[s] = jb * NB + o + bad + 1;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        a[(o + lane) * LDS + o + k] = (k <= lane) ? r[k] : T(0);
+        w[(o + k) * LDS + o + lane] = wc[k];         // column `lane` of Wdd
       }
-      a[j * LDS + j] = smk_sqrt(d);
     }
     __syncthreads();
-    const T piv = T(1) / a[j * LDS + j];
-    for (int i = j + 1 + tid; i < NB; i += 256) a[i * LDS + j] *= piv;
-    __syncthreads();
-    // rank-1 update of the trailing lower triangle
-    for (int i = j + 1 + ty; i < NB; i += 16) {
-      const T lij = a[i * LDS + j];
-      for (int k = j + 1 + tx; k <= i; k += 16) a[i * LDS + k] = fma(-lij, a[k * LDS + j], a[i * LDS + k]);
+    const int rows = NB - o - SB;                    // rows below the diagonal piece
+    if (rows > 0) {
+      // (b) X[r][k] = sum_{m<=k} A[r][o+m] * Wdd[k][m]   -> scratch, then back into a
+      for (int e = tid; e < rows * SB; e += 256) {
+        int rr = e / SB, k = e % SB;
+        const T* ar = a + (o + SB + rr) * LDS + o;
+        const T* wk = w + (o + k) * LDS + o;
+        T acc = T(0);
+        for (int m = 0; m <= k; ++m) acc = fma(ar[m], wk[m], acc);
+        t[rr * LDT + k] = acc;
+      }
+      __syncthreads();
+      for (int e = tid; e < rows * SB; e += 256) {
+        int rr = e / SB, k = e % SB;
+        a[(o + SB + rr) * LDS + o + k] = t[rr * LDT + k];
+      }
+      // (c) rank-32 update of the remaining lower triangle: a[r][c] -= X[r] . X[c]   (r >= c)
+      for (int e = tid; e < rows * rows; e += 256) {
+        int rr = e / rows, cc = e % rows;
+        if (cc > rr) continue;
+        const T* xr = t + rr * LDT;
+        const T* xc = t + cc * LDT;
+        T acc = a[(o + SB + rr) * LDS + o + SB + cc];
+#pragma unroll 8
+        for (int k = 0; k < SB; ++k) acc = fma(-xr[k], xc[k], acc);
+        a[(o + SB + rr) * LDS + o + SB + cc] = acc;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
-  // W = L^-1 by forward substitution, one column per thread (columns are independent).
-  if (tid < NB) {
-    const int c = tid;
-    for (int i = c; i < NB; ++i) {
-      T sacc = (i == c) ? T(1) : T(0);
-      for (int k = c; k < i; ++k) sacc = fma(-a[i * LDS + k], w[k * LDS + c], sacc);
-      w[i * LDS + c] = sacc / a[i * LDS + i];
+  // W = L^-1: off-diagonal 32x32 blocks by block distance d:  W_ij = -W_ii * (sum_{k=j}^{i-1} L_ik W_kj)
+  for (int d = 1; d < NSB; ++d) {
+    const int npair = NSB - d;                       // (i, j) = (j + d, j)
+    // phase 1: T_ij = sum_k L_ik W_kj  into scratch t[(pair*32 + r)][c]
+    for (int e = tid; e < npair * SB * SB; e += 256) {
+      int pr = e / (SB * SB), rr = (e / SB) % SB, cc = e % SB;
+      int j = pr, i = pr + d;
+      T acc = T(0);
+      for (int kb = j; kb < i; ++kb) {
+        const T* lrow = a + (i * SB + rr) * LDS + kb * SB;
+#pragma unroll 8
+        for (int m = 0; m < SB; ++m) acc = fma(lrow[m], w[(kb * SB + m) * LDS + j * SB + cc], acc);
+      }
+      t[(pr * SB + rr) * LDT + cc] = acc;
     }
+    __syncthreads();
+    // phase 2: W_ij = -W_ii * T_ij
+    for (int e = tid; e < npair * SB * SB; e += 256) {
+      int pr = e / (SB * SB), rr = (e / SB) % SB, cc = e % SB;
+      int j = pr, i = pr + d;
+      const T* wrow = w + (i * SB + rr) * LDS + i * SB;
+      T acc = T(0);
+      for (int m = 0; m <= rr; ++m) acc = fma(wrow[m], t[(pr * SB + m) * LDT + cc], acc);
+      w[(i * SB + rr) * LDS + j * SB + cc] = -acc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   T* Wb = winv + ((long)s * (Npad / NB) + jb) * NB * NB;
   for (int e = tid; e < NB * NB; e += 256) {
@@ -144,7 +229,7 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
   if (!winv) return -4;
   if (!info) return -5;
   const int nblk = Npad / NB;
-  const size_t dsm = 2 * (size_t)NB * (NB + 1) * sizeof(T);
+  const size_t dsm = (2 * (size_t)NB * (NB + 1) + (size_t)NB * 33) * sizeof(T);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);

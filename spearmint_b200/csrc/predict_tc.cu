@@ -106,7 +106,7 @@ __global__ void split_lower_kernel(int Npad, int ld, long total, const float* __
 // One block = 128 candidates x all n in tiles of 128, 8x8 register micro-tiles (rows = candidates, cols = n):
 // Kxt[s][c][n] as (hi, lo) float4 stores (256 B contiguous per 16 threads), mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.
 // grid = (Mc/128, S).  Output-bound: 8 B written per (3D + 25) flops.
-constexpr int kKD = 32;   // D chunk staged in shared memory
+constexpr int kKD = 16;   // D chunk staged in shared memory (17 KB total: co-resides with the 198 KB MMA block)
 
 __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, int M, int c_begin, int Mc, int D,
                                                      const float* __restrict__ X, const float* __restrict__ Cc,
@@ -115,9 +115,11 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
                                                      int Npad_alpha, float* __restrict__ khi, float* __restrict__ klo,
                                                      float* __restrict__ mu, int ldm) {
   constexpr int T = 128, LDT = T + kPad;
-  __shared__ __align__(16) float cs[kKD][LDT];    // scaled candidates   [d][cand]
-  __shared__ __align__(16) float xs[kKD][LDT];    // scaled observations [d][n]
-  __shared__ float red[16][T];
+  __shared__ __align__(16) float stage[2][kKD][LDT];
+  float (*cs)[LDT] = stage[0];                    // scaled candidates   [d][cand]
+  float (*xs)[LDT] = stage[1];                    // scaled observations [d][n]
+  float (*red)[T] = reinterpret_cast<float (*)[T]>(&stage[0][0][0]);   // [16][T] epilogue scratch (aliases the staging)
+  static_assert(16 * T <= 2 * kKD * LDT, "reduction scratch must fit in the staging buffers");
   const int s = blockIdx.y, c0 = blockIdx.x * T;  // c0 relative to the chunk
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const float* ils = inv_ls + (long)s * D;
@@ -506,19 +508,24 @@ int trtri_split(int Npad, int Np, int S, const float* L, const float* winv, floa
 // workspace: Kxt hi | Kxt lo | partial
 static size_t tc_chunk_cands(int Np, int M, int S, size_t budget) {
   size_t per_cand = 2 * (size_t)S * Np * sizeof(float);
-  size_t mc = budget / per_cand;
   size_t mpad = ((size_t)M + 127) / 128 * 128;
-  if (mc > mpad) mc = mpad;
+  size_t mc = budget / per_cand;
+  if (mc >= mpad) return mpad;                  // everything in one chunk: single buffer
+  mc = (budget / 2) / per_cand;                 // otherwise two half-size buffers (kxt of chunk i+1 overlaps MMA of i)
   mc = mc / 128 * 128;
   if (mc < 128) mc = 128;
   return mc;
+}
+static int tc_nbuf(int Np, int M, int S, size_t budget) {
+  size_t mpad = ((size_t)M + 127) / 128 * 128;
+  return tc_chunk_cands(Np, M, S, budget) >= mpad ? 1 : 2;
 }
 static const size_t kTcBudget = (size_t)20 << 30;
 
 size_t predict_tc_workspace_bytes(int Np, int M, int S) {
   size_t mc = tc_chunk_cands(Np, M, S, kTcBudget);
-  int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
-  return 2 * (size_t)S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) + 1024;
+  int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2, nbuf = tc_nbuf(Np, M, S, kTcBudget);
+  return (size_t)nbuf * 2 * S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) + 1024;
 }
 
 int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
@@ -535,37 +542,69 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   if (ldm < M) return -18;
   if (!workspace || workspace_bytes < predict_tc_workspace_bytes(Np, M, S)) return -19;
   const int Mc = (int)tc_chunk_cands(Np, M, S, kTcBudget);
+  const int nbuf = tc_nbuf(Np, M, S, kTcBudget);
   const int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
-  float* khi = reinterpret_cast<float*>(workspace);
-  float* klo = khi + (size_t)S * Mc * Np;
-  float* partial = klo + (size_t)S * Mc * Np;
+  float* khi = reinterpret_cast<float*>(workspace);                       // [nbuf][hi | lo][S][Mc][Np]
+  float* partial = khi + (size_t)nbuf * 2 * S * Mc * Np;
 
-  CUtensorMap mAhi, mAlo, mBhi, mBlo;
-  if (tc::make_map(&mAhi, khi, (uint64_t)S * Mc, Np, tc::BM) || tc::make_map(&mAlo, klo, (uint64_t)S * Mc, Np, tc::BM) ||
-      tc::make_map(&mBhi, linv_hi, (uint64_t)S * Np, Np, tc::BN) ||
-      tc::make_map(&mBlo, linv_lo, (uint64_t)S * Np, Np, tc::BN))
-    return 1999;   // SMK_ERR_CUDA range: cuTensorMapEncodeTiled unavailable / failed
+  CUtensorMap mAhi[2], mAlo[2], mBhi, mBlo;
+  for (int b = 0; b < nbuf; ++b) {
+    float* kh = khi + (size_t)b * 2 * S * Mc * Np;
+    if (tc::make_map(&mAhi[b], kh, (uint64_t)S * Mc, Np, tc::BM) ||
+        tc::make_map(&mAlo[b], kh + (size_t)S * Mc * Np, (uint64_t)S * Mc, Np, tc::BM))
+      return 1999;   // SMK_ERR_CUDA range: cuTensorMapEncodeTiled unavailable / failed
+  }
+  if (tc::make_map(&mBhi, linv_hi, (uint64_t)S * Np, Np, tc::BN) || tc::make_map(&mBlo, linv_lo, (uint64_t)S * Np, Np, tc::BN))
+    return 1999;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(tc::predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     attr = true;
   }
-  for (int c_begin = 0; c_begin < M; c_begin += Mc) {
+  // The cross-covariance of chunk i+1 is generated on an auxiliary stream while the MMA kernel consumes chunk i
+  // (two Kxt buffers; event fork/join keeps everything ordered with respect to the caller's stream).
+  static cudaStream_t aux = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_kxt[2] = {nullptr, nullptr}, ev_mma[2] = {nullptr, nullptr};
+  if (!aux) {
+    cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventCreateWithFlags(&ev_kxt[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_mma[i], cudaEventDisableTiming);
+    }
+  }
+  const bool overlap = (nbuf == 2);
+  cudaStream_t kst = overlap ? aux : st;
+  if (overlap) {
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(aux, ev_fork, 0);
+  }
+  int ci = 0;
+  for (int c_begin = 0; c_begin < M; c_begin += Mc, ++ci) {
+    const int b = overlap ? (ci & 1) : 0;
+    float* kh = khi + (size_t)b * 2 * S * Mc * Np;
+    float* kl = kh + (size_t)S * Mc * Np;
     const int mc_used = min(Mc, ((M - c_begin) + 127) / 128 * 128);
-    timing_begin("kxt_kernel", st);
-    kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, st>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
-                                                       alpha, Npad_alpha, khi, klo, mu, ldm);
-    timing_end(st);
+    if (overlap && ci >= 2) cudaStreamWaitEvent(aux, ev_mma[b], 0);      // buffer b is free again
+    timing_begin("kxt_kernel", kst);
+    kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, kst>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
+                                                        alpha, Npad_alpha, kh, kl, mu, ldm);
+    timing_end(kst);
+    if (overlap) {
+      cudaEventRecord(ev_kxt[b], aux);
+      cudaStreamWaitEvent(st, ev_kxt[b], 0);
+    }
     tc::Args a;
     a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
     a.partial = partial; a.dbg = dbg;
     long nitems = (long)S * a.ntiles * npairs;
     int grid = (int)std::min<long>(nitems, num_sms());
     timing_begin("predict_tc_kernel", st);
-    tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, a);
+    tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi[b], mAlo[b], mBhi, mBlo, a);
     timing_end(st);
     tc::finish_var_kernel<<<dim3((mc_used + 255) / 256, S), 256, 0, st>>>(M, c_begin, mc_used, S, npairs, Mc, partial,
                                                                         amp2, var, ldm);
+    if (overlap) cudaEventRecord(ev_mma[b], st);
     count_launch(3);
   }
   return check_launch("predict_tc");

@@ -410,33 +410,50 @@ class GPEIEngine(object):
 
 
 class LogLik(object):
-    """-sum(log diag chol K) - 0.5 (y-mu)' K^-1 (y-mu) for ONE hyper-parameter setting per call -- the data term of
-    every slice-sampler log-probability (OPT:635-640, 658-661, 689-692).  Buffers are allocated once; a call is
-    cov_build + potrf + forward substitution, then one small device->host read (the sampler needs the scalar to
-    decide its next step)."""
+    """-sum(log diag chol K) - 0.5 (y-mu)' K^-1 (y-mu): the data term of every slice-sampler log-probability
+    (OPT:635-640, 658-661, 689-692).  ``batch`` evaluates several hyper-parameter settings in ONE batched
+    cov_build + potrf + forward substitution (same latency as one), then one small device->host read; buffers for up
+    to ``max_batch`` matrices are allocated once."""
 
-    def __init__(self, eng, kind, comp, vals):
+    def __init__(self, eng, kind, comp, vals, max_batch=None):
         self.eng, self.kind = eng, kind
         self.X = eng.to_dev(comp)
         self.y = eng.to_dev(vals)
         self.N, self.D = self.X.shape
         Npad = _ceil(self.N, 128)
+        if max_batch is None:      # batching pays while the factorisation is latency-bound
+            max_batch = 8 if self.N <= 1024 else (6 if self.N <= 2048 else 4)
+        self.max_batch = max_batch
         dt, dev = eng.dtype, eng.device
-        self.L = torch.empty((1, Npad, Npad), dtype=dt, device=dev)
-        self.winv = torch.empty((1, Npad // eng.NB, eng.NB, eng.NB), dtype=dt, device=dev)
-        self.info = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.L = torch.empty((max_batch, Npad, Npad), dtype=dt, device=dev)
+        self.winv = torch.empty((max_batch, Npad // eng.NB, eng.NB, eng.NB), dtype=dt, device=dev)
+        self.info = torch.zeros((max_batch,), dtype=torch.int32, device=dev)
         self.calls = 0
+        self.launch_batches = 0
+
+    def batch(self, hypers):
+        """hypers: list of (mean, noise, amp2, ls).  Returns a float64 array; NaN marks a non-PD matrix."""
+        out = np.empty(len(hypers))
+        for b0 in range(0, len(hypers), self.max_batch):
+            hs = hypers[b0:b0 + self.max_batch]
+            B = len(hs)
+            eng = self.eng
+            hb = eng.hypers([(h[0], h[1], h[2], np.asarray(h[3], dtype=float)) for h in hs], self.kind)
+            fac = Factor(eng, self.kind, self.X, hb, L=self.L[:B], winv=self.winv[:B], info=self.info[:B])
+            _, sld, quad = fac.solve(self.y, F=1, want_alpha=False, want_logdet=True, want_quad=True)
+            r = torch.cat([sld.double(), quad.double().view(B), self.info[:B].double()]).cpu().numpy()
+            lp = -r[:B] - 0.5 * r[B:2 * B]
+            lp[r[2 * B:] != 0] = np.nan
+            out[b0:b0 + B] = lp
+            self.calls += B
+            self.launch_batches += 1
+        return out
 
     def __call__(self, mean, noise, amp2, ls):
-        eng = self.eng
-        hb = eng.hypers([(mean, noise, amp2, np.asarray(ls, dtype=float))], self.kind)
-        fac = Factor(eng, self.kind, self.X, hb, L=self.L, winv=self.winv, info=self.info)
-        _, sld, quad = fac.solve(self.y, F=1, want_alpha=False, want_logdet=True, want_quad=True)
-        out = torch.cat([sld.double().view(1), quad.double().view(1), self.info.double()]).cpu().numpy()
-        self.calls += 1
-        if out[2] != 0:
-            raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite" % int(out[2]))
-        return -out[0] - 0.5 * out[1]
+        v = self.batch([(mean, noise, amp2, ls)])[0]
+        if np.isnan(v):
+            raise np.linalg.LinAlgError("leading minor of the array is not positive definite")
+        return v
 
 
 class RefineContext(object):

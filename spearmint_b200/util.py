@@ -19,15 +19,37 @@ def unpack_args(arg_string):
     return {}
 
 
+SPECULATE = 3    # shrink proposals evaluated ahead of time when the log-probability supports batching
+
+
 def _slice_along(direction, x0, logprob, sigma, step_out, max_steps_out):
     """One slice-sampling move along ``direction`` (reference util.py:36-75).  RNG call order:
-    rand (interval placement), rand (slice height), then one rand per shrink proposal."""
+    rand (interval placement), rand (slice height), then one rand per shrink proposal.
+
+    If ``logprob`` has a ``prefetch(points)`` method (spearmint_b200's GPU log-likelihood), the points this move
+    will most likely visit -- 0, lower, upper and the first shrink proposals assuming no step-out -- are handed to it
+    first so they are evaluated as ONE batch.  The proposals are obtained by PEEKING the global RNG (state saved and
+    restored), so the draws consumed, the points visited and therefore the chain are exactly the reference's."""
     def lp(z):
         return logprob(direction * z + x0)
 
     upper = sigma * npr.rand()
     lower = upper - sigma
-    height = np.log(npr.rand()) + lp(0.0)
+    u_height = npr.rand()
+    if hasattr(logprob, "prefetch"):
+        state = npr.get_state()
+        peek = npr.rand(SPECULATE)
+        npr.set_state(state)
+        zs, lo, hi = [0.0, lower, upper], lower, upper
+        for r in peek:
+            z = (hi - lo) * r + lo
+            zs.append(z)
+            if z < 0:
+                lo = z
+            elif z > 0:
+                hi = z
+        logprob.prefetch([direction * z + x0 for z in zs])
+    height = np.log(u_height) + lp(0.0)
     n_lo = n_hi = 0
     if step_out:
         while lp(lower) > height and n_lo < max_steps_out:
@@ -70,3 +92,70 @@ def slice_sample(init_x, logprob, sigma=1.0, step_out=True, max_steps_out=1000, 
     direction = npr.randn(dims)
     direction = direction / np.sqrt(np.sum(direction ** 2))
     return _slice_along(direction, init_x, logprob, sigma, step_out, max_steps_out)
+
+
+class CachedLogProb(object):
+    """A slice-sampler log-probability = prior part (host) + GP log-likelihood (GPU), with a per-move cache so that
+    the points handed to ``prefetch`` are evaluated in one batched GPU call.  ``hypers_of(x)`` maps a sampler point to
+    ``None`` (prior is -inf, no likelihood evaluation -- exactly the reference's early returns) or to
+    ``((mean, noise, amp2, ls), (prior_term, ...))`` -- the terms are added in the given order."""
+
+    def __init__(self, loglik, hypers_of):
+        self.ll, self.hypers_of = loglik, hypers_of
+        self.cache = {}
+
+    @staticmethod
+    def _key(x):
+        return np.ascontiguousarray(x, dtype=np.float64).tobytes()
+
+    def prefetch(self, points):
+        self.cache = {}
+        todo, keys, priors = [], [], []
+        for x in points:
+            k = self._key(x)
+            if k in self.cache or k in keys:
+                continue
+            h = self.hypers_of(np.asarray(x, dtype=float))
+            if h is None:
+                self.cache[k] = -np.inf
+            else:
+                todo.append(h[0])
+                keys.append(k)
+                priors.append(h[1])
+        if todo:
+            vals = self.ll.batch(todo)
+            for k, v, p in zip(keys, vals, priors):
+                for t in p:                      # prior terms in the reference's order of addition
+                    v = v + t
+                self.cache[k] = v                # NaN (not PD) stays NaN and is raised on use
+
+    def __call__(self, x):
+        k = self._key(x)
+        if k in self.cache:
+            v = self.cache[k]
+            if np.isnan(v):
+                raise np.linalg.LinAlgError("leading minor of the array is not positive definite")
+            return v
+        h = self.hypers_of(np.asarray(x, dtype=float))
+        if h is None:
+            return -np.inf
+        v = self.ll(*h[0])
+        for t in h[1]:
+            v = v + t
+        return v
+
+
+def make_logprob(loglik, hypers_of):
+    """CachedLogProb (batched, speculative) when the log-likelihood can batch, else the plain sequential callable."""
+    if hasattr(loglik, "batch"):
+        return CachedLogProb(loglik, hypers_of)
+
+    def logprob(x):
+        h = hypers_of(np.asarray(x, dtype=float))
+        if h is None:
+            return -np.inf
+        v = loglik(*h[0])
+        for t in h[1]:
+            v = v + t
+        return v
+    return logprob

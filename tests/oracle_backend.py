@@ -12,14 +12,34 @@ class _State(object):
 class OracleBackend(object):
     name = "oracle"
 
-    def __init__(self):
+    def __init__(self, batched=False):
         self.loglik_calls = 0
+        self.batches = 0
+        self.batched = batched
 
     def loglik(self, kind, comp, vals):
+        outer = self
+
         def ll(mean, noise, amp2, ls):
-            self.loglik_calls += 1
+            outer.loglik_calls += 1
             return O.gp_logprob(kind, mean, noise, amp2, np.asarray(ls, float), comp, vals)
-        return ll
+        if not self.batched:
+            return ll
+
+        class Batched(object):          # same interface as engine.LogLik: exercises the speculative sampler path
+            def __call__(self, mean, noise, amp2, ls):
+                return ll(mean, noise, amp2, ls)
+
+            def batch(self, hypers):
+                outer.batches += 1
+                out = np.empty(len(hypers))
+                for i, h in enumerate(hypers):
+                    try:
+                        out[i] = ll(*h)
+                    except np.linalg.LinAlgError:
+                        out[i] = np.nan
+                return out
+        return Batched()
 
     def grid_state(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None, durs_log=None):
         st = _State()
