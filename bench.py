@@ -369,10 +369,13 @@ def main():
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-cands", type=int, default=None, help="candidates in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--samples", type=int, default=None, help="override S (experiments only)")
     ap.add_argument("--no-next", action="store_true", help="skip the chooser.next() wall-ms leg")
     ap.add_argument("--next-cpu", action="store_true", help="also time the CPU port of next() (slow)")
     args = ap.parse_args()
     D, N, M, S = WORKLOADS[args.workload]
+    if args.samples:
+        S = args.samples
     if args.impl == "reference":
         run_reference_arm(args, D, N, M, S)
     else:

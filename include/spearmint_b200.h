@@ -111,6 +111,9 @@ int smk_tc_np(int N);
 size_t smk_trtri_workspace_bytes(int Np, int S);
 int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi,
                         float* linv_lo, void* workspace, size_t workspace_bytes, void* stream);
+/* alpha[s] = K_s^-1 (y - mean[s]) from the explicit inverse (two parallel mat-vecs; OPT:543); tmp: [S][Np] floats. */
+int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
+                       const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream);
 size_t smk_predict_tc_workspace_bytes(int Np, int M, int S);
 int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
                        const float* inv_ls, const float* amp2, const float* mean, const float* linv_hi,

@@ -15,39 +15,47 @@ namespace smk {
 // Factor one NB x NB diagonal block and invert its factor, entirely on one SM (this kernel is the serial spine of
 // the factorisation: nblk launches per matrix, so its latency -- not its flops -- is what matters, above all for
 // the one-matrix-at-a-time log-likelihood calls of the slice sampler).
-//   for each 32-wide sub-block:  (a) warp 0 factors the 32 x 32 diagonal piece AND inverts it in registers with
-//   warp shuffles (no block barriers);  (b) rows below: X = A_sub * Wdd^T;  (c) rank-32 update of what is left.
+//   for each 32-wide sub-block:  (a) factor the 32 x 32 diagonal piece and invert it (block_chol_inv_32);
+//   (b) rows below: X = A_sub * Wdd^T;  (c) rank-32 update of what is left.
 //   Then W = L^-1 is assembled from the 32 x 32 inverses by block distance (d = 1, 2, ...).
 template <typename T>
 __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// lane i holds row i of a 32x32 SPD block (lower part used) in r[0..31]; on exit r = row i of L, w = COLUMN `lane` of L^-1
+// The whole block (256 threads) factors the 32x32 SPD piece at `a` (row stride lda, lower part) in place and writes its
+// inverse into `w`.  One column (resp. one row of the inverse) per step, a few elements per thread, block barriers in
+// between: the per-step latency is a barrier plus one shared-memory round trip (~100-150 cycles) instead of a
+// 30-iteration dependent loop in a single warp.  `red` is a [8][32] scratch.
 template <typename T>
-__device__ __forceinline__ void warp_chol_inv_32(T (&r)[32], T (&w)[32], int lane, int& bad) {
-#pragma unroll
+__device__ __forceinline__ void block_chol_inv_32(T* a, int lda, T* w, int ldw, T* red, int tid, int& bad) {
   for (int j = 0; j < 32; ++j) {
-    T d = shfl_t(r[j], j);
+    T d = a[j * lda + j];
     if (!(d > T(0))) { if (bad < 0) bad = j; d = T(1); }
     const T piv = smk_sqrt(d), ipiv = T(1) / piv;
-    if (lane == j) r[j] = piv;
-    else if (lane > j) r[j] *= ipiv;
+    __syncthreads();                               // everybody has read the pivot
+    if (tid == j) a[j * lda + j] = piv;
+    else if (tid > j && tid < 32) a[tid * lda + j] *= ipiv;
+    __syncthreads();
 #pragma unroll
-    for (int k = j + 1; k < 32; ++k) {
-      T lkj = shfl_t(r[j], k);
-      if (lane >= k) r[k] = fma(-r[j], lkj, r[k]);
+    for (int q = 0; q < 4; ++q) {                  // rank-1 update of the trailing lower triangle (<= 496 elements)
+      const int e = tid + q * 256, i = e >> 5, k = e & 31;
+      if (k > j && k <= i) a[i * lda + k] = fma(-a[i * lda + j], a[k * lda + j], a[i * lda + k]);
     }
+    __syncthreads();
   }
-  // forward substitution for column `lane` of the inverse: w_i = (delta - sum_{k<i} L_ik w_k) / L_ii
-#pragma unroll
+  // inverse by rows: W[i][c] = (delta_ic - sum_{c<=k<i} L[i][k] W[k][c]) / L[i][i], k split over 8 thread groups
+  const int c = tid & 31, part = tid >> 5;
   for (int i = 0; i < 32; ++i) {
-    T acc = (i == lane) ? T(1) : T(0);
+    T acc = T(0);
+    for (int k = c + part; k < i; k += 8) acc = fma(a[i * lda + k], w[k * ldw + c], acc);
+    red[part * 32 + c] = acc;
+    __syncthreads();
+    if (part == 0) {
+      T sum = T(0);
 #pragma unroll
-    for (int k = 0; k < i; ++k) {
-      T lik = shfl_t(r[k], i);              // L[i][k], uniform over the warp
-      acc = fma(-lik, w[k], acc);           // w[k] is 0 for k < lane
+      for (int g = 0; g < 8; ++g) sum += red[g * 32 + c];
+      w[i * ldw + c] = (c <= i) ? (((c == i) ? T(1) : T(0)) - sum) / a[i * lda + i] : T(0);
     }
-    T lii = shfl_t(r[i], i);
-    w[i] = (i >= lane) ? acc / lii : T(0);
+    __syncthreads();
   }
 }
 
@@ -61,32 +69,31 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(int Npad, int jb, T* __
   T* w = a + NB * LDS;                     // [NB][LDS] its inverse (lower)
   T* t = w + NB * LDS;                     // [NB][SB+1] scratch for the panel / inverse assembly
   constexpr int LDT = SB + 1;
-  const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x, tid = threadIdx.x;
   T* Ab = A + (long)s * Npad * Npad + (long)jb * NB * Npad + (long)jb * NB;
 
-  for (int e = tid; e < NB * NB; e += 256) {
-    int i = e / NB, k = e % NB;
-    a[i * LDS + k] = (k <= i) ? Ab[(long)i * Npad + k] : T(0);
-    w[i * LDS + k] = T(0);
+  for (int e0 = tid; e0 < NB * NB; e0 += 256 * 8) {
+    T v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int e = e0 + q * 256, i = e / NB, k = e % NB;
+      v[q] = (e < NB * NB && k <= i) ? Ab[(long)i * Npad + k] : T(0);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int e = e0 + q * 256, i = e / NB, k = e % NB;
+      if (e < NB * NB) { a[i * LDS + k] = v[q]; w[i * LDS + k] = T(0); }
+    }
   }
   __syncthreads();
 
   for (int sb = 0; sb < NSB; ++sb) {
     const int o = sb * SB;
-    // (a) 32x32 diagonal piece: factor + invert in registers of warp 0
-    if (warp == 0) {
-      T r[32], wc[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) r[k] = a[(o + lane) * LDS + o + k];
+    // (a) 32x32 diagonal piece: factor + invert
+    {
       int bad = -1;
-      warp_chol_inv_32<T>(r, wc, lane, bad);
-      bad = __reduce_max_sync(0xffffffffu, bad);     // identical on all lanes anyway
-      if (bad >= 0 && lane == 0 && info[s] == 0) info[s] = jb * NB + o + bad + 1;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        a[(o + lane) * LDS + o + k] = (k <= lane) ? r[k] : T(0);
-        w[(o + k) * LDS + o + lane] = wc[k];         // column `lane` of Wdd
-      }
+      block_chol_inv_32<T>(a + o * LDS + o, LDS, w + o * LDS + o, LDS, t, tid, bad);
+      if (bad >= 0 && tid == 0 && info[s] == 0) info[s] = jb * NB + o + bad + 1;
     }
     __syncthreads();
     const int rows = NB - o - SB;                    // rows below the diagonal piece

@@ -18,15 +18,19 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace smk {
 
 // ================================================================================================= trtri (SIMT)
-// X = L^-1 by block columns: X_JJ = W_JJ;  X_IJ = -W_II * sum_{J<=K<I} L_IK X_KJ.   grid = (nblk, S).
-__global__ void __launch_bounds__(256, 2) trtri_kernel(int Npad, int ldx, const float* __restrict__ L,
-                                                        const float* __restrict__ winv, float* X) {
+// X = L^-1, right-looking by block rows (the critical path is nblk small steps, so it scales down to a handful of
+// matrices per GPU):   for K = 0..nblk-1:
+//   finalize : X_KJ = W_KK * acc_KJ (J < K),  X_KK = W_KK          acc_KJ holds  -sum_{K'<K} L_KK' X_K'J
+//   update   : acc_IJ -= L_IK * X_KJ  for I > K, J <= K
+__global__ void __launch_bounds__(256, 2) trtri_finalize_kernel(int Npad, int ldx, int K, const float* __restrict__ winv,
+                                                                 float* X) {
   using C = Cfg<float>;
   constexpr int NB = C::NB, TM = C::TM, TN = C::TN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -34,57 +38,82 @@ __global__ void __launch_bounds__(256, 2) trtri_kernel(int Npad, int ldx, const 
   float (*Ts)[NB + kPad] = reinterpret_cast<float (*)[NB + kPad]>(smem_raw + sizeof(TileSmem<float>));
   const int nblk = Npad / NB, J = blockIdx.x, s = blockIdx.y;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const float* Ls = L + (long)s * Npad * Npad;
-  const float* Ws = winv + (long)s * nblk * NB * NB;
-  float* Xs = X + (long)s * ldx * ldx;
-  for (int I = J; I < nblk; ++I) {
-    float acc[TM][TN];
-#pragma unroll
-    for (int r = 0; r < TM; ++r)
-#pragma unroll
-      for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
-    if (I == J) {
-      const float* W = Ws + (long)J * NB * NB;
-#pragma unroll
-      for (int r = 0; r < TM; ++r)
-#pragma unroll
-        for (int g = 0; g < TN / 4; ++g) {
-          V4<float> v = ld4(W + (long)tile_row(ty, r) * NB + g * 64 + tx * 4);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[r][g * 4 + e] = v.v[e];
-        }
-    } else {
-      TileGemm<float, Lay::KContig, Lay::MContig, true>::run(acc, Ls + (long)I * NB * Npad + (long)J * NB, Npad,
-                                                            Xs + (long)J * NB * ldx + (long)J * NB, ldx,
-                                                            (I - J) * NB, sm);
-      __syncthreads();
-#pragma unroll
-      for (int r = 0; r < TM; ++r)
-#pragma unroll
-        for (int g = 0; g < TN / 4; ++g) {
-          V4<float> v;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
-          st4(&Ts[tile_row(ty, r)][g * 64 + tx * 4], v);
-        }
-#pragma unroll
-      for (int r = 0; r < TM; ++r)
-#pragma unroll
-        for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
-      TileGemm<float, Lay::KContig, Lay::MContig, false>::run_bsmem(acc, Ws + (long)I * NB * NB, NB, &Ts[0][0],
-                                                                   NB + kPad, NB, sm);
-    }
+  const float* W = winv + ((long)s * nblk + K) * NB * NB;
+  float* Xt = X + (long)s * ldx * ldx + (long)K * NB * ldx + (long)J * NB;
+  float acc[TM][TN];
+  if (J == K) {
 #pragma unroll
     for (int r = 0; r < TM; ++r)
 #pragma unroll
       for (int g = 0; g < TN / 4; ++g) {
-        V4<float> v;
+        V4<float> v = ld4(W + (long)tile_row(ty, r) * NB + g * 64 + tx * 4);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
-        st4(Xs + (long)(I * NB + tile_row(ty, r)) * ldx + J * NB + g * 64 + tx * 4, v);
+        for (int e = 0; e < 4; ++e) acc[r][g * 4 + e] = v.v[e];
       }
-    __syncthreads();
+  } else {
+    // stage the accumulated tile in shared memory (it is overwritten in place), then multiply by W_KK
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int g = 0; g < TN / 4; ++g) {
+        V4<float> v = ld4(Xt + (long)tile_row(ty, r) * ldx + g * 64 + tx * 4);
+        st4(&Ts[tile_row(ty, r)][g * 64 + tx * 4], v);
+      }
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
+    TileGemm<float, Lay::KContig, Lay::MContig, false>::run_bsmem(acc, W, NB, &Ts[0][0], NB + kPad, NB, sm);
   }
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int g = 0; g < TN / 4; ++g) {
+      V4<float> v;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
+      st4(Xt + (long)tile_row(ty, r) * ldx + g * 64 + tx * 4, v);
+    }
+}
+
+// grid = (nblk-K-1, K+1, S):  X_IJ -= L_IK * X_KJ
+__global__ void __launch_bounds__(256, 2) trtri_update_kernel(int Npad, int ldx, int K, const float* __restrict__ L,
+                                                               float* X) {
+  using C = Cfg<float>;
+  constexpr int NB = C::NB, TM = C::TM, TN = C::TN;
+  __shared__ TileSmem<float> sm;
+  const int I = K + 1 + blockIdx.x, J = blockIdx.y, s = blockIdx.z;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const float* Lik = L + (long)s * Npad * Npad + (long)I * NB * Npad + (long)K * NB;
+  float* Xs = X + (long)s * ldx * ldx;
+  float* Xij = Xs + (long)I * NB * ldx + (long)J * NB;
+  const float* Xkj = Xs + (long)K * NB * ldx + (long)J * NB;
+  float acc[TM][TN];
+  if (K == J) {            // first contribution to this tile: start from zero (the buffer is not pre-cleared)
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
+  } else {
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int g = 0; g < TN / 4; ++g) {
+        V4<float> v = ld4(Xij + (long)tile_row(ty, r) * ldx + g * 64 + tx * 4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[r][g * 4 + e] = v.v[e];
+      }
+  }
+  TileGemm<float, Lay::KContig, Lay::MContig, true>::run(acc, Lik, Npad, Xkj, ldx, NB, sm);
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int g = 0; g < TN / 4; ++g) {
+      V4<float> v;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
+      st4(Xij + (long)tile_row(ty, r) * ldx + g * 64 + tx * 4, v);
+    }
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -100,6 +129,41 @@ __global__ void split_lower_kernel(int Npad, int ld, long total, const float* __
   float h = tf32_hi(x);
   hi[e] = h;
   lo[e] = x - h;
+}
+
+// ================================================================================================= alpha via Linv
+// alpha = K^-1 (y - mean) = Linv^T (Linv (y - mean)): two fully parallel matrix-vector products with the explicit
+// inverse (hi + lo is the exact float32 value) instead of the serial block substitution of solve.cu.
+__global__ void __launch_bounds__(256) linv_mv_kernel(int N, int Np, const float* __restrict__ hi,
+                                                      const float* __restrict__ lo, const float* __restrict__ y,
+                                                      const float* __restrict__ mean, float* __restrict__ t) {
+  const int s = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= Np) return;
+  const long base = ((long)s * Np + row) * Np;
+  const float mu = mean[s];
+  float acc = 0.f;
+  for (int k = lane; k <= row && k < N; k += 32) acc = fmaf(hi[base + k] + lo[base + k], y[k] - mu, acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) t[(long)s * Np + row] = (row < N) ? acc : 0.f;
+}
+// alpha[c] = sum_{r >= c} Linv[r][c] t[r]; block = 64 columns x 4 row-phases
+__global__ void __launch_bounds__(256) linv_mtv_kernel(int N, int Np, int ld_alpha, const float* __restrict__ hi,
+                                                       const float* __restrict__ lo, const float* __restrict__ t,
+                                                       float* __restrict__ alpha) {
+  __shared__ float red[4][64];
+  const int s = blockIdx.y, cl = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  const float* th = t + (long)s * Np;
+  const long base = (long)s * Np * Np + c;
+  float acc = 0.f;
+  if (c < N)
+    for (int r = (c & ~3) + ph; r < N; r += 4)
+      if (r >= c) acc = fmaf(hi[base + (long)r * Np] + lo[base + (long)r * Np], th[r], acc);
+  red[ph][cl] = acc;
+  __syncthreads();
+  if (ph == 0 && c < ld_alpha) alpha[(long)s * ld_alpha + c] = (c < N) ? red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl] : 0.f;
 }
 
 // ================================================================================================= kxt (SIMT)
@@ -493,31 +557,56 @@ int trtri_split(int Npad, int Np, int S, const float* L, const float* winv, floa
   const size_t dsm = sizeof(TileSmem<float>) + sizeof(float) * 128 * (128 + kPad);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(trtri_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
     attr = true;
   }
+  const int nblk = Npad / 128;
   timing_begin("trtri_kernel", st);
-  trtri_kernel<<<dim3(Npad / 128, S), 256, dsm, st>>>(Npad, Np, L, winv, X);
+  for (int K = 0; K < nblk; ++K) {
+    trtri_finalize_kernel<<<dim3(K + 1, S), 256, dsm, st>>>(Npad, Np, K, winv, X);
+    if (K + 1 < nblk) trtri_update_kernel<<<dim3(nblk - K - 1, K + 1, S), 256, 0, st>>>(Npad, Np, K, L, X);
+  }
   timing_end(st);
+  count_launch(2 * nblk - 1);
   const long total = (long)S * Np * Np;
   split_lower_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Npad, Np, total, X, linv_hi, linv_lo);
-  count_launch(2);
+  count_launch(1);
   return check_launch("trtri_split");
 }
 
+int linv_alpha(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y, const float* mean,
+               float* alpha, int ld_alpha, float* tmp, cudaStream_t st) {
+  if (N <= 0 || Np < N) return -1;
+  if (S <= 0) return -3;
+  if (!linv_hi || !linv_lo || !y || !mean || !alpha || !tmp) return -4;
+  if (ld_alpha < N) return -9;
+  linv_mv_kernel<<<dim3((Np + 7) / 8, S), 256, 0, st>>>(N, Np, linv_hi, linv_lo, y, mean, tmp);
+  linv_mtv_kernel<<<dim3((ld_alpha + 63) / 64, S), 256, 0, st>>>(N, Np, ld_alpha, linv_hi, linv_lo, tmp, alpha);
+  count_launch(2);
+  return check_launch("linv_alpha");
+}
+
+// kxt(i+1) / MMA(i) overlap on two streams: measured SLOWER on B200 (both kernels share the 1 kW power cap: the clock
+// fell from 1515 to 1372 MHz and the step went from 474 to 543 ms), so it is opt-in (SMK_TC_OVERLAP=1).
+static bool tc_overlap_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SMK_TC_OVERLAP"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 // workspace: Kxt hi | Kxt lo | partial
 static size_t tc_chunk_cands(int Np, int M, int S, size_t budget) {
   size_t per_cand = 2 * (size_t)S * Np * sizeof(float);
   size_t mpad = ((size_t)M + 127) / 128 * 128;
   size_t mc = budget / per_cand;
   if (mc >= mpad) return mpad;                  // everything in one chunk: single buffer
-  mc = (budget / 2) / per_cand;                 // otherwise two half-size buffers (kxt of chunk i+1 overlaps MMA of i)
+  if (tc_overlap_enabled()) mc = (budget / 2) / per_cand;   // two half-size buffers (kxt of chunk i+1 overlaps MMA of i)
   mc = mc / 128 * 128;
   if (mc < 128) mc = 128;
   return mc;
 }
 static int tc_nbuf(int Np, int M, int S, size_t budget) {
   size_t mpad = ((size_t)M + 127) / 128 * 128;
+  if (!tc_overlap_enabled()) return 1;
   return tc_chunk_cands(Np, M, S, budget) >= mpad ? 1 : 2;
 }
 static const size_t kTcBudget = (size_t)20 << 30;

@@ -89,6 +89,17 @@ class Factor(object):
             self._linv = (hi, lo, Np)
         return self._linv
 
+    def alpha_via_linv(self, y):
+        """alpha = Linv^T Linv (y - mean), [S][1][Npad]; needs the explicit inverse (tensor-core predict path)."""
+        eng, L = self.eng, _lib.lib()
+        hi, lo, Np = self.linv()
+        S = self.hb.S
+        alpha = torch.empty((S, 1, self.Npad), dtype=torch.float32, device=eng.device)
+        tmp = torch.empty((S, Np), dtype=torch.float32, device=eng.device)
+        check(L.smk_linv_alpha_f32(self.N, Np, S, ptr(hi), ptr(lo), ptr(y), ptr(self.hb.mean), ptr(alpha), self.Npad,
+                                   ptr(tmp), eng.stream()), "linv_alpha")
+        return alpha
+
     def check_pd(self):
         """The reference lets spla.cholesky raise LinAlgError (SURVEY 8b 'Errors'); so do we."""
         info = self.info.cpu().numpy()
@@ -292,7 +303,10 @@ class GPEIEngine(object):
             fac = self.factor(kind, Xo, hb)
             self._t1("cov_potrf", t)
             t = self._t0()
-            alpha, _, _ = fac.solve(yd, F=1)
+            if self.predict_impl == "tc":
+                alpha = fac.alpha_via_linv(yd)       # two parallel mat-vecs with the explicit inverse
+            else:
+                alpha, _, _ = fac.solve(yd, F=1)
             self._t1("chol_solve", t)
             p.fac, p.alpha, p.F = fac, alpha, 1
             p.bests = torch.full((hb.S, 1), best_val, dtype=self.dtype, device=self.device)
