@@ -114,11 +114,14 @@ int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* wi
 /* alpha[s] = K_s^-1 (y - mean[s]) from the explicit inverse (two parallel mat-vecs; OPT:543); tmp: [S][Np] floats. */
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream);
-size_t smk_predict_tc_workspace_bytes(int Np, int M, int S);
+size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F);
+/* F > 1 with alpha_f [S][F][Npad_alpha] and mu_f [S][F][ldm] non-NULL: additionally the fantasy means
+ * mu_f[s][f][j] = cov(X, C_j)' alpha_f[s][f] + mean[s]  (OPT:609) as a second tcgen05 GEMM on the same Kxt chunk. */
 int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
                        const float* inv_ls, const float* amp2, const float* mean, const float* linv_hi,
                        const float* linv_lo, const float* alpha, int Npad_alpha, float* mu, float* var, int ldm,
-                       void* workspace, size_t workspace_bytes, float* dbg_beta, void* stream);
+                       void* workspace, size_t workspace_bytes, float* dbg_beta, int F, const float* alpha_f,
+                       float* mu_f, void* stream);
 
 /* ---- (4b) cross mean only: mu[s][f][j] = cov(X, C_j)' alpha[s][f] + mean[s]
  *          time-GP mean of EI-per-second (PSEC:442-459) and fantasy means (OPT:609).

@@ -66,10 +66,11 @@ size_t topk_workspace_bytes(int, int);
 int tc_np(int);
 size_t trtri_workspace_bytes(int, int);
 int trtri_split(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
-size_t predict_tc_workspace_bytes(int, int, int);
+size_t predict_tc_workspace_bytes(int, int, int, int);
 int linv_alpha(int, int, int, const float*, const float*, const float*, const float*, float*, int, float*, cudaStream_t);
 int predict_tc(int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
-               const float*, const float*, const float*, int, float*, float*, int, void*, size_t, float*, cudaStream_t);
+               const float*, const float*, const float*, int, float*, float*, int, void*, size_t, float*, int,
+               const float*, float*, cudaStream_t);
 size_t predict_workspace_bytes_any(int, int);
 
 }  // namespace smk
@@ -155,7 +156,7 @@ int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* wi
                         void* workspace, size_t workspace_bytes, void* stream) {
   return trtri_split(Npad, Np, S, L, winv, linv_hi, linv_lo, workspace, workspace_bytes, ST(stream));
 }
-size_t smk_predict_tc_workspace_bytes(int Np, int M, int S) { return predict_tc_workspace_bytes(Np, M, S); }
+size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F) { return predict_tc_workspace_bytes(Np, M, S, F); }
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream) {
   return linv_alpha(N, Np, S, linv_hi, linv_lo, y, mean, alpha, ld_alpha, tmp, ST(stream));
@@ -163,9 +164,10 @@ int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* 
 int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
                        const float* inv_ls, const float* amp2, const float* mean, const float* linv_hi,
                        const float* linv_lo, const float* alpha, int Npad_alpha, float* mu, float* var, int ldm,
-                       void* workspace, size_t workspace_bytes, float* dbg_beta, void* stream) {
+                       void* workspace, size_t workspace_bytes, float* dbg_beta, int F, const float* alpha_f,
+                       float* mu_f, void* stream) {
   return predict_tc(kind, N, Np, M, D, S, X, C, inv_ls, amp2, mean, linv_hi, linv_lo, alpha, Npad_alpha, mu, var, ldm,
-                    workspace, workspace_bytes, dbg_beta, ST(stream));
+                    workspace, workspace_bytes, dbg_beta, F, alpha_f, mu_f, ST(stream));
 }
 
 int smk_cross_mean_f32(int kind, int N, int Npad, int M, int D, int S, int F, const float* X, const float* C,

@@ -166,6 +166,20 @@ __global__ void __launch_bounds__(256) linv_mtv_kernel(int N, int Np, int ld_alp
   if (ph == 0 && c < ld_alpha) alpha[(long)s * ld_alpha + c] = (c < N) ? red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl] : 0.f;
 }
 
+// alpha^T (hi, lo) for the rectangular fantasy-mean GEMM: out[s][f][n], f padded to Fp rows, n padded to Np (zeros)
+__global__ void alpha_split_kernel(int N, int Np, int F, int Fp, int Npad_alpha, long total,
+                                   const float* __restrict__ alpha, float* __restrict__ hi, float* __restrict__ lo) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  int n = (int)(e % Np);
+  long sf = e / Np;
+  int f = (int)(sf % Fp), s = (int)(sf / Fp);
+  float x = (f < F && n < N) ? alpha[((long)s * F + f) * Npad_alpha + n] : 0.f;
+  float h = tf32_hi(x);
+  hi[e] = h;
+  lo[e] = x - h;
+}
+
 // ================================================================================================= kxt (SIMT)
 // One block = 128 candidates x all n in tiles of 128, 8x8 register micro-tiles (rows = candidates, cols = n):
 // Kxt[s][c][n] as (hi, lo) float4 stores (256 B contiguous per 16 threads), mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.
@@ -354,6 +368,11 @@ struct Args {
   int S, Np, Mc, ntiles, npairs, ngroups, ldp;   // Mc = candidates per chunk (multiple of 128); ldp = partial stride
   float* partial;                                 // [npairs][S][ldp]
   float* dbg;                                     // optional [S][Mc][Np] dump of beta^T (tests only)
+  // rectangular mode (fantasy means, OPT:609): B = alpha^T [S][ngroups*256][Np], full k range, one group per item,
+  // the epilogue stores  D[c][f] + mean[s]  to mu_f[s][f][c_begin + c]  instead of reducing squares
+  int rect, F, M, c_begin, ldm;
+  const float* mean;
+  float* mu_f;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -400,9 +419,9 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         const int tile = (int)(st % p.ntiles), s = (int)(st / p.ntiles);
         for (int h = 0; h < 2; ++h) {
           const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
-          if (h == 1 && g == pr) break;                 // middle group of an odd count
-          const int nk = (g + 1) * (BN / BK);
-          const int rowA = s * p.Mc + tile * BM, rowB = s * p.Np + g * BN;
+          if (h == 1 && (p.rect || g == pr)) break;     // rect: one group per item; middle group of an odd count
+          const int nk = p.rect ? p.Np / BK : (g + 1) * (BN / BK);
+          const int rowA = s * p.Mc + tile * BM, rowB = (s * p.ngroups + g) * BN;
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* sb = base + stage * STAGE_BYTES;
@@ -424,8 +443,8 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         const int pr = (int)(w % p.npairs);
         for (int h = 0; h < 2; ++h) {
           const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
-          if (h == 1 && g == pr) break;
-          const int nk = (g + 1) * (BN / BK);
+          if (h == 1 && (p.rect || g == pr)) break;
+          const int nk = p.rect ? p.Np / BK : (g + 1) * (BN / BK);
           mbar_wait(&tempty[buf], bphase ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d = tmem_base + buf * BN;
@@ -463,7 +482,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       float acc = 0.f;
       for (int h = 0; h < 2; ++h) {
         const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
-        if (h == 1 && g == pr) break;
+        if (h == 1 && (p.rect || g == pr)) break;
         mbar_wait(&tfull[buf], bphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
@@ -477,7 +496,17 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
             float v = __uint_as_float(r[j]);
             acc = fmaf(v, v, acc);
           }
-          if (p.dbg) {
+          if (p.rect) {
+            const int gc = p.c_begin + tile * BM + cand_in_tile;
+            if (gc < p.M) {
+              const float mu0 = p.mean[s];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int f = g * BN + c0 + j;
+                if (f < p.F) p.mu_f[((long)s * p.F + f) * p.ldm + gc] = __uint_as_float(r[j]) + mu0;
+              }
+            }
+          } else if (p.dbg) {
             float* o = p.dbg + ((long)s * p.Mc + tile * BM + cand_in_tile) * p.Np + g * BN + c0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
@@ -489,7 +518,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         buf ^= 1;
         if (buf == 0) bphase ^= 1;
       }
-      p.partial[((long)pr * p.S + s) * p.ldp + tile * BM + cand_in_tile] = acc;
+      if (!p.rect) p.partial[((long)pr * p.S + s) * p.ldp + tile * BM + cand_in_tile] = acc;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -611,16 +640,19 @@ static int tc_nbuf(int Np, int M, int S, size_t budget) {
 }
 static const size_t kTcBudget = (size_t)20 << 30;
 
-size_t predict_tc_workspace_bytes(int Np, int M, int S) {
+static int fant_rows(int F) { return F > 1 ? ((F + tc::BN - 1) / tc::BN) * tc::BN : 0; }
+
+size_t predict_tc_workspace_bytes(int Np, int M, int S, int F) {
   size_t mc = tc_chunk_cands(Np, M, S, kTcBudget);
   int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2, nbuf = tc_nbuf(Np, M, S, kTcBudget);
-  return (size_t)nbuf * 2 * S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) + 1024;
+  return (size_t)nbuf * 2 * S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) +
+         2 * (size_t)S * fant_rows(F) * Np * sizeof(float) + 1024;
 }
 
 int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
                const float* amp2, const float* mean, const float* linv_hi, const float* linv_lo, const float* alpha,
                int Npad_alpha, float* mu, float* var, int ldm, void* workspace, size_t workspace_bytes, float* dbg,
-               cudaStream_t st) {
+               int F, const float* alpha_f, float* mu_f, cudaStream_t st) {
   if (kind < 0 || kind > 3) return -1;
   if (N <= 0) return -2;
   if (Np < N || Np % tc::BN) return -3;
@@ -629,12 +661,24 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   if (S <= 0) return -6;
   if (!X || !Cc || !inv_ls || !amp2 || !mean || !linv_hi || !linv_lo || !alpha || !mu || !var) return -7;
   if (ldm < M) return -18;
-  if (!workspace || workspace_bytes < predict_tc_workspace_bytes(Np, M, S)) return -19;
+  const bool fant = (F > 1 && alpha_f && mu_f);
+  if (!workspace || workspace_bytes < predict_tc_workspace_bytes(Np, M, S, fant ? F : 1)) return -19;
   const int Mc = (int)tc_chunk_cands(Np, M, S, kTcBudget);
   const int nbuf = tc_nbuf(Np, M, S, kTcBudget);
   const int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
   float* khi = reinterpret_cast<float*>(workspace);                       // [nbuf][hi | lo][S][Mc][Np]
   float* partial = khi + (size_t)nbuf * 2 * S * Mc * Np;
+  const int Fp = fant ? fant_rows(F) : 0;
+  float* ahi = partial + (size_t)npairs * S * Mc;               // alpha^T hi | lo  [S][Fp][Np]
+  float* alo = ahi + (size_t)S * Fp * Np;
+  CUtensorMap mFhi, mFlo;
+  if (fant) {
+    const long total = (long)S * Fp * Np;
+    alpha_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, Np, F, Fp, Npad_alpha, total, alpha_f, ahi, alo);
+    count_launch();
+    if (tc::make_map(&mFhi, ahi, (uint64_t)S * Fp, Np, tc::BN) || tc::make_map(&mFlo, alo, (uint64_t)S * Fp, Np, tc::BN))
+      return 1999;
+  }
 
   CUtensorMap mAhi[2], mAlo[2], mBhi, mBlo;
   for (int b = 0; b < nbuf; ++b) {
@@ -686,6 +730,7 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     tc::Args a;
     a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
     a.partial = partial; a.dbg = dbg;
+    a.rect = 0; a.F = 0; a.M = M; a.c_begin = c_begin; a.ldm = ldm; a.mean = mean; a.mu_f = nullptr;
     long nitems = (long)S * a.ntiles * npairs;
     int grid = (int)std::min<long>(nitems, num_sms());
     timing_begin("predict_tc_kernel", st);
@@ -693,8 +738,18 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     timing_end(st);
     tc::finish_var_kernel<<<dim3((mc_used + 255) / 256, S), 256, 0, st>>>(M, c_begin, mc_used, S, npairs, Mc, partial,
                                                                         amp2, var, ldm);
-    if (overlap) cudaEventRecord(ev_mma[b], st);
     count_launch(3);
+    if (fant) {      // fantasy means: same Kxt chunk against alpha^T, rectangular k range (OPT:609)
+      tc::Args r = a;
+      r.rect = 1; r.F = F; r.mu_f = mu_f; r.ngroups = Fp / tc::BN; r.npairs = r.ngroups;
+      long nit = (long)S * r.ntiles * r.npairs;
+      int gr = (int)std::min<long>(nit, num_sms());
+      timing_begin("predict_tc_kernel_rect", st);
+      tc::predict_tc_kernel<<<gr, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi[b], mAlo[b], mFhi, mFlo, r);
+      timing_end(st);
+      count_launch();
+    }
+    if (overlap) cudaEventRecord(ev_mma[b], st);
   }
   return check_launch("predict_tc");
 }

@@ -222,8 +222,9 @@ class GPEIEngine(object):
                                           ptr(hb.amp2), None, ptr(out), M, self.stream()), "cov_build")
         return out
 
-    def predict(self, kind, fac, C_dev, alpha, impl=None, dbg_beta=None):
-        """Predictive mean / variance at the candidates for every sample of the factor batch."""
+    def predict(self, kind, fac, C_dev, alpha, impl=None, dbg_beta=None, alpha_f=None, F=1):
+        """Predictive mean / variance at the candidates for every sample of the factor batch.  With ``alpha_f``
+        ([S][F][Npad], tensor-core path) also the F fantasy means, returned as a third tensor [S][F][ldm]."""
         hb, dt = fac.hb, self.dtype
         M = C_dev.shape[0]
         ldm = _ceil(M, 128)
@@ -232,14 +233,18 @@ class GPEIEngine(object):
         if (impl or self.predict_impl) == "tc" and isinstance(fac, Factor):
             L = _lib.lib()
             hi, lo, Np = fac.linv()
-            nb = L.smk_predict_tc_workspace_bytes(Np, M, hb.S)
+            nb = L.smk_predict_tc_workspace_bytes(Np, M, hb.S, F if alpha_f is not None else 1)
             if self._ws_tc is None or self._ws_tc.numel() < nb:
                 self._ws_tc = None
                 self._ws_tc = torch.empty((nb,), dtype=torch.uint8, device=self.device)
+            mu_f = torch.empty((hb.S, F, ldm), dtype=dt, device=self.device) if alpha_f is not None else None
             check(L.smk_predict_tc_f32(KINDS[kind], fac.N, Np, M, fac.D, hb.S, ptr(fac.X), ptr(C_dev), ptr(hb.inv_ls),
                                        ptr(hb.amp2), ptr(hb.mean), ptr(hi), ptr(lo), ptr(alpha), fac.Npad, ptr(mu),
-                                       ptr(var), ldm, ptr(self._ws_tc), nb, ptr(dbg_beta), self.stream()),
+                                       ptr(var), ldm, ptr(self._ws_tc), nb, ptr(dbg_beta),
+                                       F if alpha_f is not None else 1, ptr(alpha_f), ptr(mu_f), self.stream()),
                   "predict_tc")
+            if alpha_f is not None:
+                return mu, var, ldm, mu_f
             return mu, var, ldm
         nb = _lib.lib().smk_predict_workspace_bytes(self.esize, fac.Npad)
         ws = self.workspace(nb)
@@ -362,12 +367,15 @@ class GPEIEngine(object):
             tfac, ta = p.time
             log_time = self.cross_mean(kind, tfac, Cd, ta, 1).view(tfac.hb.S, ldm)
         t = self._t0()
-        mu, var, _ = self.predict(kind, fac, Cd, p.pred_alpha)                     # OPT:544-548 / 605-610
-        self._t1("predict", t)
-        if p.P > 0:
-            mu = self.cross_mean(kind, fac, Cd, p.alpha, p.F)                      # OPT:609
+        if p.P > 0 and self.predict_impl == "tc" and p.F > 1:
+            _, var, _, mu = self.predict(kind, fac, Cd, p.pred_alpha, alpha_f=p.alpha, F=p.F)   # OPT:605-610
         else:
-            mu = mu.view(hb.S, 1, ldm)
+            mu, var, _ = self.predict(kind, fac, Cd, p.pred_alpha)                 # OPT:544-548 / 605-610
+            if p.P > 0:
+                mu = self.cross_mean(kind, fac, Cd, p.alpha, p.F)                  # OPT:609
+            else:
+                mu = mu.view(hb.S, 1, ldm)
+        self._t1("predict", t)
         t = self._t0()
         out = self.ei_sweep(M, hb.S, p.F, mu, var, ldm, p.bests, log_time, want_matrix, ei_sum)
         self._t1("ei_sweep", t)
