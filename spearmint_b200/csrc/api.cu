@@ -232,7 +232,7 @@ struct DevBuf {
     return p;
   }
 };
-DevBuf g_in, g_fac, g_winv, g_alpha, g_mv, g_ws, g_ei;
+DevBuf g_in, g_fac, g_winv, g_alpha, g_mv, g_ws, g_ei, g_linv, g_ws2;
 std::vector<float> g_host;
 }  // namespace
 
@@ -245,7 +245,7 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   if (D <= 0) return -4;
   if (S <= 0) return -5;
   if (!comp || !cand || !vals || !ls || !amp2 || !noise || !mean || !ei_out) return -6;
-  const int Npad = smk_npad(N), NB = Cfg<float>::NB, ldm = ((M + 127) / 128) * 128;
+  const int Npad = smk_npad(N), NB = Cfg<float>::NB, ldm = ((M + 127) / 128) * 128, Np = smk_tc_np(N);
   cudaStream_t st = 0;
   // ---- pack all small inputs into one pinned-size host block: X | C | y | inv_ls | amp2 | noise | mean | best
   const size_t nX = (size_t)N * D, nC = (size_t)M * D, nH = (size_t)S * D;
@@ -267,9 +267,12 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   float* alpha = (float*)g_alpha.get((size_t)S * Npad * sizeof(float));
   float* mv = (float*)g_mv.get(2 * (size_t)S * ldm * sizeof(float));
   float* ei = (float*)g_ei.get((size_t)S * ldm * sizeof(float) + S * sizeof(int));
-  const size_t wsb = smk_predict_workspace_bytes(4, Npad);
+  const size_t wsb = smk_predict_tc_workspace_bytes(Np, M, S, 1);
   void* ws = g_ws.get(wsb);
-  if (!d || !fac || !winv || !alpha || !mv || !ei || !ws) {
+  const size_t ws2b = smk_trtri_workspace_bytes(Np, S) + (size_t)S * Np * sizeof(float);
+  void* ws2 = g_ws2.get(ws2b);
+  float* linv = (float*)g_linv.get(2 * (size_t)S * Np * Np * sizeof(float));
+  if (!d || !fac || !winv || !alpha || !mv || !ei || !ws || !ws2 || !linv) {
     snprintf(g_err, sizeof(g_err), "cudaMalloc failed");
     return SMK_ERR_CUDA;
   }
@@ -280,9 +283,14 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   int rc;
   if ((rc = smk_cov_build_f32(kind, N, N, D, S, dX, nullptr, dil, da, dn, fac, Npad, st))) return rc;
   if ((rc = smk_potrf_lower_batched_f32(Npad, S, fac, winv, info, st))) return rc;
-  if ((rc = smk_chol_solve_f32(N, Npad, S, 1, fac, winv, dy, 0, N, dm, alpha, nullptr, nullptr, st))) return rc;
-  if ((rc = smk_predict_f32(kind, N, Npad, M, D, S, dX, dC, dil, da, dm, fac, winv, alpha, mv, mv + (size_t)S * ldm,
-                            ldm, ws, wsb, st)))
+  // tensor-core path: explicit inverse (split), alpha by two mat-vecs, tcgen05 3xTF32 predict
+  float* lhi = linv;
+  float* llo = linv + (size_t)S * Np * Np;
+  float* tmp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws2) + smk_trtri_workspace_bytes(Np, S));
+  if ((rc = smk_trtri_split_f32(Npad, Np, S, fac, winv, lhi, llo, ws2, smk_trtri_workspace_bytes(Np, S), st))) return rc;
+  if ((rc = smk_linv_alpha_f32(N, Np, S, lhi, llo, dy, dm, alpha, Npad, tmp, st))) return rc;
+  if ((rc = smk_predict_tc_f32(kind, N, Np, M, D, S, dX, dC, dil, da, dm, lhi, llo, alpha, Npad, mv,
+                               mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, st)))
     return rc;
   if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, st))) return rc;
   std::vector<float> hout((size_t)S * ldm);
