@@ -84,6 +84,15 @@ int smk_chol_solve_f64(int N, int Npad, int S, int F, const double* L, const dou
                        const double* y, long long y_stride, int ldy, const double* mean,
                        double* alpha, double* sum_log_diag, double* quad, void* stream);
 
+/* ---- (3b) GP log marginal likelihood by augmentation (slice-sampler logprob, OPT:637-640, 659-661, 690-692)
+ * smk_loglik_set_rhs_*: A[s][N][0:N] = y - mean[s], A[s][N][N] = 1e30 in covariance storage with Npad > N, BEFORE
+ * smk_potrf_lower_batched_*; the factorisation then leaves L^-1 (y - mean) in row N.
+ * smk_loglik_finish_*: sum_log_diag[s] = sum_{i<N} log L_ii;  quad[s] = |L[N][0:N]|^2 = (y-mean)' K^-1 (y-mean).   */
+int smk_loglik_set_rhs_f32(int N, int Npad, int S, const float* y, const float* mean, float* A, void* stream);
+int smk_loglik_set_rhs_f64(int N, int Npad, int S, const double* y, const double* mean, double* A, void* stream);
+int smk_loglik_finish_f32(int N, int Npad, int S, const float* L, float* sum_log_diag, float* quad, void* stream);
+int smk_loglik_finish_f64(int N, int Npad, int S, const double* L, double* sum_log_diag, double* quad, void* stream);
+
 /* ---- (4) fused predict: cross-covariance tiles generated on the fly -> blocked triangular
  *          solve against L -> predictive mean and variance.  beta and Kx never reach HBM as
  *          N x M matrices.            (OPT:535 cand_cross, OPT:544 beta, OPT:547-548 func_m/func_v)

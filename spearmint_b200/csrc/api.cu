@@ -50,6 +50,10 @@ int potrf_lower_batched(int, int, T*, T*, int*, cudaStream_t);
 template <typename T>
 int chol_solve(int, int, int, int, const T*, const T*, const T*, long long, int, const T*, T*, T*, T*, cudaStream_t);
 template <typename T>
+int loglik_set_rhs(int, int, int, const T*, const T*, T*, cudaStream_t);
+template <typename T>
+int loglik_finish(int, int, int, const T*, T*, T*, cudaStream_t);
+template <typename T>
 int predict(int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, const T*,
             const T*, T*, T*, int, void*, size_t, cudaStream_t);
 template <typename T>
@@ -131,6 +135,19 @@ int smk_chol_solve_f64(int N, int Npad, int S, int F, const double* L, const dou
                        long long y_stride, int ldy, const double* mean, double* alpha, double* sum_log_diag,
                        double* quad, void* stream) {
   return chol_solve<double>(N, Npad, S, F, L, winv, y, y_stride, ldy, mean, alpha, sum_log_diag, quad, ST(stream));
+}
+
+int smk_loglik_set_rhs_f32(int N, int Npad, int S, const float* y, const float* mean, float* A, void* stream) {
+  return loglik_set_rhs<float>(N, Npad, S, y, mean, A, ST(stream));
+}
+int smk_loglik_set_rhs_f64(int N, int Npad, int S, const double* y, const double* mean, double* A, void* stream) {
+  return loglik_set_rhs<double>(N, Npad, S, y, mean, A, ST(stream));
+}
+int smk_loglik_finish_f32(int N, int Npad, int S, const float* L, float* sld, float* quad, void* stream) {
+  return loglik_finish<float>(N, Npad, S, L, sld, quad, ST(stream));
+}
+int smk_loglik_finish_f64(int N, int Npad, int S, const double* L, double* sld, double* quad, void* stream) {
+  return loglik_finish<double>(N, Npad, S, L, sld, quad, ST(stream));
 }
 
 size_t smk_predict_workspace_bytes(int elem_bytes, int Npad) { return predict_workspace_bytes_any(elem_bytes, Npad); }

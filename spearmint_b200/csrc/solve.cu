@@ -232,6 +232,61 @@ int chol_solve(int N, int Npad, int S, int F, const T* L, const T* winv, const T
   return check_launch("chol_solve");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Log-likelihood by augmentation: put r = y - mean in row N of the (padded) covariance before factoring it,
+//   [ K  . ]   [ L        0 ] [ L^T  L^-1 r ]
+//   [ r' c ] = [ (L^-1r)' * ] [ 0    *      ]
+// so the Cholesky panel/trailing kernels perform the forward substitution as part of the factorisation (one extra
+// row in a block row that exists anyway) and   quad = |L[N, 0:N]|^2,   sum_log_diag = sum_{i<N} log L_ii.
+// Needs Npad > N (the caller pads to ceil128(N + 1)).  Replaces the serial chol_solve on the slice-sampler path.
+template <typename T>
+__global__ void loglik_set_rhs_kernel(int N, int Npad, const T* __restrict__ y, const T* __restrict__ mean, T* A) {
+  const int s = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  T* row = A + (long)s * Npad * Npad + (long)N * Npad;
+  if (n < N) row[n] = y[n] - mean[s];
+  else if (n == N) row[n] = T(1e30);            // pivot of the augmented row: c - quad must stay positive
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) loglik_finish_kernel(int N, int Npad, const T* __restrict__ L, T* __restrict__ sld,
+                                                             T* __restrict__ quad) {
+  __shared__ T red8[8];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const T* Ls = L + (long)s * Npad * Npad;
+  T a = T(0), q = T(0);
+  for (int n = tid; n < N; n += 256) {
+    a += smk_log(Ls[(long)n * Npad + n]);
+    T v = Ls[(long)N * Npad + n];
+    q = fma(v, v, q);
+  }
+  a = block_sum(a, red8);
+  q = block_sum(q, red8);
+  if (tid == 0) { sld[s] = a; quad[s] = q; }
+}
+
+template <typename T>
+int loglik_set_rhs(int N, int Npad, int S, const T* y, const T* mean, T* A, cudaStream_t st) {
+  if (N <= 0 || Npad <= N || Npad % kNpadMult) return -2;
+  if (S <= 0) return -3;
+  if (!y || !mean || !A) return -4;
+  loglik_set_rhs_kernel<T><<<dim3((N + 256) / 256, S), 256, 0, st>>>(N, Npad, y, mean, A);
+  count_launch();
+  return check_launch("loglik_set_rhs");
+}
+template <typename T>
+int loglik_finish(int N, int Npad, int S, const T* L, T* sld, T* quad, cudaStream_t st) {
+  if (N <= 0 || Npad <= N) return -2;
+  if (S <= 0) return -3;
+  if (!L || !sld || !quad) return -4;
+  loglik_finish_kernel<T><<<S, 256, 0, st>>>(N, Npad, L, sld, quad);
+  count_launch();
+  return check_launch("loglik_finish");
+}
+template int loglik_set_rhs<float>(int, int, int, const float*, const float*, float*, cudaStream_t);
+template int loglik_set_rhs<double>(int, int, int, const double*, const double*, double*, cudaStream_t);
+template int loglik_finish<float>(int, int, int, const float*, float*, float*, cudaStream_t);
+template int loglik_finish<double>(int, int, int, const double*, double*, double*, cudaStream_t);
+
 template int chol_solve<float>(int, int, int, int, const float*, const float*, const float*, long long, int,
                                const float*, float*, float*, float*, cudaStream_t);
 template int chol_solve<double>(int, int, int, int, const double*, const double*, const double*, long long, int,

@@ -434,36 +434,43 @@ class GPEIEngine(object):
 class LogLik(object):
     """-sum(log diag chol K) - 0.5 (y-mu)' K^-1 (y-mu): the data term of every slice-sampler log-probability
     (OPT:635-640, 658-661, 689-692).  ``batch`` evaluates several hyper-parameter settings in ONE batched
-    cov_build + potrf + forward substitution (same latency as one), then one small device->host read; buffers for up
-    to ``max_batch`` matrices are allocated once."""
+    cov_build + potrf (same latency as one) and one small device->host read.  The residual rides along as an extra
+    row of the covariance (csrc/solve.cu: augmentation), so the factorisation itself performs the forward
+    substitution -- no serial triangular solve.  Buffers for ``max_batch`` matrices are allocated once."""
 
     def __init__(self, eng, kind, comp, vals, max_batch=None):
         self.eng, self.kind = eng, kind
         self.X = eng.to_dev(comp)
         self.y = eng.to_dev(vals)
         self.N, self.D = self.X.shape
-        Npad = _ceil(self.N, 128)
+        self.Npad = _ceil(self.N + 1, 128)          # room for the augmented row
         if max_batch is None:      # batching pays while the factorisation is latency-bound
             max_batch = 8 if self.N <= 1024 else (6 if self.N <= 2048 else 4)
         self.max_batch = max_batch
         dt, dev = eng.dtype, eng.device
-        self.L = torch.empty((max_batch, Npad, Npad), dtype=dt, device=dev)
-        self.winv = torch.empty((max_batch, Npad // eng.NB, eng.NB, eng.NB), dtype=dt, device=dev)
+        self.L = torch.empty((max_batch, self.Npad, self.Npad), dtype=dt, device=dev)
+        self.winv = torch.empty((max_batch, self.Npad // eng.NB, eng.NB, eng.NB), dtype=dt, device=dev)
         self.info = torch.zeros((max_batch,), dtype=torch.int32, device=dev)
+        self.out = torch.empty((2, max_batch), dtype=dt, device=dev)
         self.calls = 0
         self.launch_batches = 0
 
     def batch(self, hypers):
         """hypers: list of (mean, noise, amp2, ls).  Returns a float64 array; NaN marks a non-PD matrix."""
         out = np.empty(len(hypers))
+        eng, dt, N, Npad = self.eng, self.eng.dtype, self.N, self.Npad
         for b0 in range(0, len(hypers), self.max_batch):
             hs = hypers[b0:b0 + self.max_batch]
             B = len(hs)
-            eng = self.eng
             hb = eng.hypers([(h[0], h[1], h[2], np.asarray(h[3], dtype=float)) for h in hs], self.kind)
-            fac = Factor(eng, self.kind, self.X, hb, L=self.L[:B], winv=self.winv[:B], info=self.info[:B])
-            _, sld, quad = fac.solve(self.y, F=1, want_alpha=False, want_logdet=True, want_quad=True)
-            r = torch.cat([sld.double(), quad.double().view(B), self.info[:B].double()]).cpu().numpy()
+            st = eng.stream()
+            check(fn("smk_cov_build", dt)(KINDS[self.kind], N, N, self.D, B, ptr(self.X), None, ptr(hb.inv_ls),
+                                          ptr(hb.amp2), ptr(hb.noise), ptr(self.L), Npad, st), "cov_build")
+            check(fn("smk_loglik_set_rhs", dt)(N, Npad, B, ptr(self.y), ptr(hb.mean), ptr(self.L), st), "loglik_set_rhs")
+            check(fn("smk_potrf_lower_batched", dt)(Npad, B, ptr(self.L), ptr(self.winv), ptr(self.info), st), "potrf")
+            check(fn("smk_loglik_finish", dt)(N, Npad, B, ptr(self.L), ptr(self.out[0]), ptr(self.out[1]), st),
+                  "loglik_finish")
+            r = torch.cat([self.out[0, :B].double(), self.out[1, :B].double(), self.info[:B].double()]).cpu().numpy()
             lp = -r[:B] - 0.5 * r[B:2 * B]
             lp[r[2 * B:] != 0] = np.nan
             out[b0:b0 + B] = lp
