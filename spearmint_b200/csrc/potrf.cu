@@ -193,14 +193,15 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(int Npad, int jb, T* _
 }
 
 // --------------------------------------------------------------------------------------- trailing
-// A_IK -= L_Ij * L_Kj^T for jb < K <= I   (grid.x = I - jb - 1, grid.y = K - jb - 1)
+// A_IK -= L[I, jb:jb+kd] * L[K, jb:jb+kd]^T   for c0 <= K <= I   (grid.x = I - c0, grid.y = K - c0), kd = depth in
+// block columns: the driver updates block columns in PAIRS (rank 2*NB), halving the accumulator load/store traffic.
 template <typename T>
-__global__ void __launch_bounds__(256, 2) potrf_trailing_kernel(int Npad, int jb, T* __restrict__ A) {
+__global__ void __launch_bounds__(256, 2) potrf_trailing_kernel(int Npad, int jb, int kd, int c0, T* __restrict__ A) {
   using C = Cfg<T>;
   constexpr int NB = C::NB;
   if (blockIdx.y > blockIdx.x) return;
   __shared__ TileSmem<T> sm;
-  const int s = blockIdx.z, I = jb + 1 + blockIdx.x, K = jb + 1 + blockIdx.y;
+  const int s = blockIdx.z, I = c0 + blockIdx.x, K = c0 + blockIdx.y;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   T* As = A + (long)s * Npad * Npad;
   T* Aik = As + (long)I * NB * Npad + (long)K * NB;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(256, 2) potrf_trailing_kernel(int Npad, int jb
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[r][g * 4 + e] = v.v[e];
     }
-  TileGemm<T, Lay::KContig, Lay::KContig, true>::run(acc, Lij, Npad, Lkj, Npad, NB, sm);
+  TileGemm<T, Lay::KContig, Lay::KContig, true>::run(acc, Lij, Npad, Lkj, Npad, kd * NB, sm);
 #pragma unroll
   for (int r = 0; r < C::TM; ++r)
 #pragma unroll
@@ -243,15 +244,22 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
     attr_done = true;
   }
   cudaMemsetAsync(info, 0, sizeof(int) * S, st);
-  for (int jb = 0; jb < nblk; ++jb) {
+  // Block columns in pairs (jb, jb+1): factor jb, bring only column jb+1 up to date (rank NB), factor jb+1, then ONE
+  // rank-2*NB update of everything to the right.
+  for (int jb = 0; jb < nblk; jb += 2) {
     potrf_diag_kernel<T><<<S, 256, dsm, st>>>(Npad, jb, A, winv, info);
     count_launch();
-    const int rem = nblk - jb - 1;
-    if (rem > 0) {
-      potrf_panel_kernel<T><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, A, winv);
-      potrf_trailing_kernel<T><<<dim3(rem, rem, S), 256, 0, st>>>(Npad, jb, A);
-      count_launch(2);
-    }
+    int rem = nblk - jb - 1;
+    if (rem <= 0) break;
+    potrf_panel_kernel<T><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, A, winv);
+    potrf_trailing_kernel<T><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, 1, jb + 1, A);      // column jb+1 only
+    potrf_diag_kernel<T><<<S, 256, dsm, st>>>(Npad, jb + 1, A, winv, info);
+    count_launch(3);
+    rem = nblk - jb - 2;
+    if (rem <= 0) break;
+    potrf_panel_kernel<T><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb + 1, A, winv);
+    potrf_trailing_kernel<T><<<dim3(rem, rem, S), 256, 0, st>>>(Npad, jb, 2, jb + 2, A);   // rank 2*NB, columns >= jb+2
+    count_launch(2);
   }
   return check_launch("potrf_lower_batched");
 }
