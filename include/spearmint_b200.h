@@ -120,6 +120,16 @@ int smk_tc_np(int N);
 size_t smk_trtri_workspace_bytes(int Np, int S);
 int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi,
                         float* linv_lo, void* workspace, size_t workspace_bytes, void* stream);
+/* Tensor-core variants of the N^3 steps (float32, 3xTF32, same outputs):
+ *   smk_potrf_lower_batched_tc_f32 : left-looking blocked Cholesky, the rank-(jb*128) update of every block-column pair
+ *       runs on tcgen05 (workspace: 2*S*Npad*Npad floats for the tf32 hi/lo copies of the finished panels).
+ *   smk_trtri_split_tc_f32 : L^-1 by row blocks, X[K,:] = -(W_KK L[K,:]) X on tcgen05; writes linv_hi/linv_lo like
+ *       smk_trtri_split_f32 (workspace: smk_trtri_tc_workspace_bytes).                                          */
+int smk_potrf_lower_batched_tc_f32(int Npad, int S, float* A, float* winv, int* info, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+size_t smk_trtri_tc_workspace_bytes(int Npad, int Np, int S);
+int smk_trtri_split_tc_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi,
+                           float* linv_lo, void* workspace, size_t workspace_bytes, void* stream);
 /* alpha[s] = K_s^-1 (y - mean[s]) from the explicit inverse (two parallel mat-vecs; OPT:543); tmp: [S][Np] floats. */
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream);

@@ -55,6 +55,9 @@ SIGNATURES = {
     "smk_trtri_workspace_bytes": ([_i, _i], _sz),
     "smk_trtri_split_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "smk_predict_tc_workspace_bytes": ([_i, _i, _i, _i], _sz),
+    "smk_potrf_lower_batched_tc_f32": ([_i, _i, _p, _p, _p, _p, _sz, _p], _i),
+    "smk_trtri_tc_workspace_bytes": ([_i, _i, _i], _sz),
+    "smk_trtri_split_tc_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "smk_linv_alpha_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p], _i),
     "smk_predict_tc_f32": ([_i] * 6 + [_p] * 8 + [_i, _p, _p, _i, _p, _sz, _p, _i, _p, _p, _p], _i),
 }

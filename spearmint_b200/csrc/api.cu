@@ -71,6 +71,9 @@ int tc_np(int);
 size_t trtri_workspace_bytes(int, int);
 int trtri_split(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
 size_t predict_tc_workspace_bytes(int, int, int, int);
+int potrf_lower_batched_tc(int, int, float*, float*, int*, float*, float*, cudaStream_t);
+size_t trtri_tc_workspace_bytes(int, int, int);
+int trtri_split_tc(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
 int linv_alpha(int, int, int, const float*, const float*, const float*, const float*, float*, int, float*, cudaStream_t);
 int predict_tc(int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
                const float*, const float*, const float*, int, float*, float*, int, void*, size_t, float*, int,
@@ -174,6 +177,17 @@ int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* wi
   return trtri_split(Npad, Np, S, L, winv, linv_hi, linv_lo, workspace, workspace_bytes, ST(stream));
 }
 size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F) { return predict_tc_workspace_bytes(Np, M, S, F); }
+int smk_potrf_lower_batched_tc_f32(int Npad, int S, float* A, float* winv, int* info, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!workspace || workspace_bytes < 2 * (size_t)S * Npad * Npad * sizeof(float)) return -6;
+  float* lhi = reinterpret_cast<float*>(workspace);
+  return potrf_lower_batched_tc(Npad, S, A, winv, info, lhi, lhi + (size_t)S * Npad * Npad, ST(stream));
+}
+size_t smk_trtri_tc_workspace_bytes(int Npad, int Np, int S) { return trtri_tc_workspace_bytes(Npad, Np, S); }
+int smk_trtri_split_tc_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi, float* linv_lo,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return trtri_split_tc(Npad, Np, S, L, winv, linv_hi, linv_lo, workspace, workspace_bytes, ST(stream));
+}
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream) {
   return linv_alpha(N, Np, S, linv_hi, linv_lo, y, mean, alpha, ld_alpha, tmp, ST(stream));

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(int Npad, int jb, T* __
 // L_Ij = A_Ij * W_jj^T  (one block per row tile I > jb)
 template <typename T>
 __global__ void __launch_bounds__(256) potrf_panel_kernel(int Npad, int jb, T* __restrict__ A,
-                                                           const T* __restrict__ winv) {
+                                                           const T* __restrict__ winv, T* __restrict__ hi = nullptr,
+                                                           T* __restrict__ lo = nullptr) {
   using C = Cfg<T>;
   constexpr int NB = C::NB;
   __shared__ TileSmem<T> sm;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(int Npad, int jb, T* _
 #pragma unroll
     for (int c = 0; c < C::TN; ++c) acc[r][c] = T(0);
   TileGemm<T, Lay::KContig, Lay::KContig, false>::run(acc, Aij, Npad, W, NB, NB, sm);
+  const long off = (long)s * Npad * Npad + (long)I * NB * Npad + (long)jb * NB;
 #pragma unroll
   for (int r = 0; r < C::TM; ++r)
 #pragma unroll
@@ -188,7 +190,20 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(int Npad, int jb, T* _
       V4<T> v;
 #pragma unroll
       for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
-      st4(Aij + (long)tile_row(ty, r) * Npad + tile_col(tx, g * 4), v);
+      const long o = (long)tile_row(ty, r) * Npad + tile_col(tx, g * 4);
+      st4(Aij + o, v);
+      if (sizeof(T) == 4 && hi != nullptr) {     // tf32 hi/lo copies of the finished panel (operands of the tcgen05 update)
+        V4<T> h, l;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x = (float)v.v[e];
+          float xh = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+          h.v[e] = (T)xh;
+          l.v[e] = (T)(x - xh);
+        }
+        st4(hi + off + o, h);
+        st4(lo + off + o, l);
+      }
     }
 }
 
@@ -262,6 +277,46 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
     count_launch(2);
   }
   return check_launch("potrf_lower_batched");
+}
+
+// ---- left-looking variant with the rank-(jb*NB) update of each block-column pair on the tensor cores (float32):
+//   update(jb)  : A[rows >= jb][cols jb, jb+1] -= L[rows, 0:jb] L[jb:jb+2, 0:jb]^T     tcgen05 3xTF32 (predict_tc.cu)
+//   diag, panel : as above; the panel kernel also writes the tf32 hi/lo copies the next updates read through TMA
+//   column jb+1 is brought up to date w.r.t. column jb by one rank-NB SIMT update.
+int tc_chol_update(int Npad, int S, int jb, int ncols, float* A, const float* lhi, const float* llo, cudaStream_t st);
+
+int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, float* lhi, float* llo, cudaStream_t st) {
+  constexpr int NB = Cfg<float>::NB;
+  if (Npad <= 0 || Npad % kNpadMult) return -1;
+  if (S <= 0) return -2;
+  if (!A || !winv || !info || !lhi || !llo) return -3;
+  const int nblk = Npad / NB;
+  const size_t dsm = (2 * (size_t)NB * (NB + 1) + (size_t)NB * 33) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(potrf_diag_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    attr_done = true;
+  }
+  cudaMemsetAsync(info, 0, sizeof(int) * S, st);
+  for (int jb = 0; jb < nblk; jb += 2) {
+    if (jb > 0) {
+      int rc = tc_chol_update(Npad, S, jb, (jb + 1 < nblk) ? 2 * NB : NB, A, lhi, llo, st);
+      if (rc) return rc;
+    }
+    potrf_diag_kernel<float><<<S, 256, dsm, st>>>(Npad, jb, A, winv, info);
+    count_launch();
+    int rem = nblk - jb - 1;
+    if (rem <= 0) break;
+    potrf_panel_kernel<float><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, A, winv, lhi, llo);
+    potrf_trailing_kernel<float><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, 1, jb + 1, A);
+    potrf_diag_kernel<float><<<S, 256, dsm, st>>>(Npad, jb + 1, A, winv, info);
+    count_launch(3);
+    rem = nblk - jb - 2;
+    if (rem <= 0) break;
+    potrf_panel_kernel<float><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb + 1, A, winv, lhi, llo);
+    count_launch();
+  }
+  return check_launch("potrf_lower_batched_tc");
 }
 
 template int potrf_lower_batched<float>(int, int, float*, float*, int*, cudaStream_t);

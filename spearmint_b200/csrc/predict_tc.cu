@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -373,7 +374,52 @@ struct Args {
   int rect, F, M, c_begin, ldm;
   const float* mean;
   float* mu_f;
+  // mode 2 (left-looking Cholesky update, potrf_tc): C[(jb+m)-th block row][block cols jb, jb+1] -= L[.., 0:jb] L[jb.., 0:jb]^T
+  // mode 3 (triangular inverse, row block K): X[K, 0:K*128] = -Lt * X[0:K*128, 0:K*128], stored as X and X^T, hi/lo
+  int mode;            // 0 tri (predict), 1 rect (fantasy means), 2 Cholesky update, 3 trtri row block
+  int Npad, jb, ncols; // mode 2: factor leading dimension, first block column of the pair, valid columns (128 | 256)
+  float* Cmat;         // mode 2: [S][Npad][Npad] matrix being factored
+  int K;               // mode 3: row block
+  float *xhi, *xlo, *xthi, *xtlo;   // mode 3 outputs, each [S][Np][Np]
 };
+
+// One unit of MMA work: A rows / B rows / k range (in elements) of a single accumulator pass.
+struct Item { int valid, rowA, rowB, k0, nk, s, tile, g, pr; };
+
+__device__ __forceinline__ Item get_item(const Args& p, long w, int h) {
+  Item it;
+  it.valid = 0; it.rowA = it.rowB = it.k0 = it.nk = it.s = it.tile = it.g = it.pr = 0;
+  if (p.mode <= 1) {
+    it.pr = (int)(w % p.npairs);
+    const long st = w / p.npairs;
+    it.tile = (int)(st % p.ntiles);
+    it.s = (int)(st / p.ntiles);
+    it.g = (h == 0) ? it.pr : p.ngroups - 1 - it.pr;
+    if (h == 1 && (p.mode == 1 || it.g == it.pr)) return it;   // rect: one group per item; middle group of an odd count
+    it.nk = (p.mode == 1) ? p.Np / BK : (it.g + 1) * (BN / BK);
+    it.rowA = it.s * p.Mc + it.tile * BM;
+    it.rowB = (it.s * p.ngroups + it.g) * BN;
+    it.valid = 1;
+  } else if (p.mode == 2) {
+    if (h == 1) return it;
+    it.tile = (int)(w % p.ntiles);                 // block row jb + tile
+    it.s = (int)(w / p.ntiles);
+    it.rowA = it.s * p.Npad + (p.jb + it.tile) * BM;
+    it.rowB = it.s * p.Npad + p.jb * BM;            // block rows jb and jb+1 (256 rows)
+    it.nk = p.jb * BM / BK;
+    it.valid = 1;
+  } else {
+    if (h == 1) return it;
+    it.tile = (int)(w % p.ntiles);                 // column tile t of X (256 columns)
+    it.s = (int)(w / p.ntiles);
+    it.rowA = it.s * BM;                            // Lt: [S][128][ld]
+    it.rowB = it.s * p.Np + it.tile * BN;           // X^T rows j
+    it.k0 = it.tile * BN;
+    it.nk = (p.K * BM - it.tile * BN) / BK;
+    it.valid = 1;
+  }
+  return it;
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
@@ -404,32 +450,28 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  const long nitems = (long)p.S * p.ntiles * p.npairs;
-  // item -> (s, tile, pair): consecutive items share (s, tile) so the pair-blocks of one candidate tile run
+  const long nitems = (long)p.S * p.ntiles * (p.mode <= 1 ? p.npairs : 1);
+  // mode 0 item order (s, tile, pair): consecutive items share (s, tile) so the pair-blocks of one candidate tile run
   // concurrently on neighbouring SMs and hit L2 for the Kxt slab.
   if (warp == 0) {
     if (lane == 0) {
-      const uint64_t hintA = 0x12F0000000000000ull;   // EVICT_FIRST: Kxt is streamed
-      const uint64_t hintB = 0x14F0000000000000ull;   // EVICT_LAST : Linv is re-read by every tile of the sample
+      const uint64_t hintA = 0x12F0000000000000ull;   // EVICT_FIRST: the A operand is streamed
+      const uint64_t hintB = 0x14F0000000000000ull;   // EVICT_LAST : the B operand is re-read by many items
       int stage = 0;
       uint32_t phase = 0;
       for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
-        const int pr = (int)(w % p.npairs);
-        const long st = w / p.npairs;
-        const int tile = (int)(st % p.ntiles), s = (int)(st / p.ntiles);
         for (int h = 0; h < 2; ++h) {
-          const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
-          if (h == 1 && (p.rect || g == pr)) break;     // rect: one group per item; middle group of an odd count
-          const int nk = p.rect ? p.Np / BK : (g + 1) * (BN / BK);
-          const int rowA = s * p.Mc + tile * BM, rowB = (s * p.ngroups + g) * BN;
-          for (int kc = 0; kc < nk; ++kc) {
+          const Item it = get_item(p, w, h);
+          if (!it.valid) break;
+          for (int kc = 0; kc < it.nk; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* sb = base + stage * STAGE_BYTES;
+            const int kk = it.k0 + kc * BK;
             mbar_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(&mAhi, &full[stage], sb, kc * BK, rowA, hintA);
-            tma_load_2d(&mAlo, &full[stage], sb + A_BYTES, kc * BK, rowA, hintA);
-            tma_load_2d(&mBhi, &full[stage], sb + 2 * A_BYTES, kc * BK, rowB, hintB);
-            tma_load_2d(&mBlo, &full[stage], sb + 2 * A_BYTES + B_BYTES, kc * BK, rowB, hintB);
+            tma_load_2d(&mAhi, &full[stage], sb, kk, it.rowA, hintA);
+            tma_load_2d(&mAlo, &full[stage], sb + A_BYTES, kk, it.rowA, hintA);
+            tma_load_2d(&mBhi, &full[stage], sb + 2 * A_BYTES, kk, it.rowB, hintB);
+            tma_load_2d(&mBlo, &full[stage], sb + 2 * A_BYTES + B_BYTES, kk, it.rowB, hintB);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -440,15 +482,13 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0, buf = 0, bphase = 0;
       for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
-        const int pr = (int)(w % p.npairs);
         for (int h = 0; h < 2; ++h) {
-          const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
-          if (h == 1 && (p.rect || g == pr)) break;
-          const int nk = p.rect ? p.Np / BK : (g + 1) * (BN / BK);
+          const Item it = get_item(p, w, h);
+          if (!it.valid) break;
           mbar_wait(&tempty[buf], bphase ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d = tmem_base + buf * BN;
-          for (int kc = 0; kc < nk; ++kc) {
+          for (int kc = 0; kc < it.nk; ++kc) {
             mbar_wait(&full[stage], phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
@@ -471,18 +511,16 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       }
     }
   } else {
-    // epilogue warps 2..5 own TMEM lane quarters (warp % 4)
+    // epilogue warps 2..5 own TMEM lane quarters (warp % 4); lane = row of the accumulator tile
     const int q = warp & 3;
-    const int cand_in_tile = q * 32 + lane;
+    const int row = q * 32 + lane;
     uint32_t buf = 0, bphase = 0;
     for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
-      const int pr = (int)(w % p.npairs);
-      const long st = w / p.npairs;
-      const int tile = (int)(st % p.ntiles), s = (int)(st / p.ntiles);
       float acc = 0.f;
+      Item it0 = get_item(p, w, 0);
       for (int h = 0; h < 2; ++h) {
-        const int g = (h == 0) ? pr : p.ngroups - 1 - pr;
-        if (h == 1 && (p.rect || g == pr)) break;
+        const Item it = get_item(p, w, h);
+        if (!it.valid) break;
         mbar_wait(&tfull[buf], bphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
@@ -491,25 +529,61 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           uint32_t r[32];
           tmem_ld32(t0 + c0, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (p.mode == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]);
-            acc = fmaf(v, v, acc);
-          }
-          if (p.rect) {
-            const int gc = p.c_begin + tile * BM + cand_in_tile;
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]);
+              acc = fmaf(v, v, acc);
+            }
+            if (p.dbg) {
+              float* o = p.dbg + ((long)it.s * p.Mc + it.tile * BM + row) * p.Np + it.g * BN + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+            }
+          } else if (p.mode == 1) {
+            const int gc = p.c_begin + it.tile * BM + row;
             if (gc < p.M) {
-              const float mu0 = p.mean[s];
+              const float mu0 = p.mean[it.s];
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const int f = g * BN + c0 + j;
-                if (f < p.F) p.mu_f[((long)s * p.F + f) * p.ldm + gc] = __uint_as_float(r[j]) + mu0;
+                const int f = it.g * BN + c0 + j;
+                if (f < p.F) p.mu_f[((long)it.s * p.F + f) * p.ldm + gc] = __uint_as_float(r[j]) + mu0;
               }
             }
-          } else if (p.dbg) {
-            float* o = p.dbg + ((long)s * p.Mc + tile * BM + cand_in_tile) * p.Np + g * BN + c0;
+          } else if (p.mode == 2) {
+            if (c0 < p.ncols) {
+              float* c = p.Cmat + ((long)it.s * p.Npad + (long)(p.jb + it.tile) * BM + row) * p.Npad + (long)p.jb * BM + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+              for (int j = 0; j < 32; j += 4) {
+                float4 v = *reinterpret_cast<float4*>(c + j);
+                v.x -= __uint_as_float(r[j]); v.y -= __uint_as_float(r[j + 1]);
+                v.z -= __uint_as_float(r[j + 2]); v.w -= __uint_as_float(r[j + 3]);
+                *reinterpret_cast<float4*>(c + j) = v;
+              }
+            }
+          } else {
+            const int jcol = it.tile * BN + c0;                 // first column of this chunk
+            if (jcol < p.K * BM) {
+              const long xr = ((long)it.s * p.Np + (long)p.K * BM + row) * p.Np + jcol;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float v[4], hh[4], ll[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[e] = -__uint_as_float(r[j + e]);
+                  hh[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                  ll[e] = v[e] - hh[e];
+                }
+                *reinterpret_cast<float4*>(p.xhi + xr + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                *reinterpret_cast<float4*>(p.xlo + xr + j) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {                   // transposed copy: lanes = consecutive k -> coalesced
+                  const long xt = ((long)it.s * p.Np + jcol + j + e) * p.Np + (long)p.K * BM + row;
+                  p.xthi[xt] = hh[e];
+                  p.xtlo[xt] = ll[e];
+                }
+              }
+            }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -518,7 +592,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         buf ^= 1;
         if (buf == 0) bphase ^= 1;
       }
-      if (!p.rect) p.partial[((long)pr * p.S + s) * p.ldp + tile * BM + cand_in_tile] = acc;
+      if (p.mode == 0) p.partial[((long)it0.pr * p.S + it0.s) * p.ldp + it0.tile * BM + row] = acc;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -601,6 +675,135 @@ int trtri_split(int Npad, int Np, int S, const float* L, const float* winv, floa
   split_lower_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Npad, Np, total, X, linv_hi, linv_lo);
   count_launch(1);
   return check_launch("trtri_split");
+}
+
+// ---------------------------------------------------------------------------------- tensor-core Cholesky update
+static void tc_args_init(tc::Args& a) {
+  memset(&a, 0, sizeof(a));
+}
+
+int tc_chol_update(int Npad, int S, int jb, int ncols, float* A, const float* lhi, const float* llo, cudaStream_t st) {
+  CUtensorMap mAhi, mAlo, mBhi, mBlo;
+  if (tc::make_map(&mAhi, lhi, (uint64_t)S * Npad, Npad, tc::BM) || tc::make_map(&mAlo, llo, (uint64_t)S * Npad, Npad, tc::BM) ||
+      tc::make_map(&mBhi, lhi, (uint64_t)S * Npad, Npad, tc::BN) || tc::make_map(&mBlo, llo, (uint64_t)S * Npad, Npad, tc::BN))
+    return 1999;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc::predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    attr = true;
+  }
+  tc::Args a;
+  tc_args_init(a);
+  a.mode = 2; a.S = S; a.Npad = Npad; a.jb = jb; a.ncols = ncols; a.Cmat = A;
+  a.ntiles = Npad / tc::BM - jb; a.npairs = 1; a.ngroups = 1;
+  long nitems = (long)S * a.ntiles;
+  int grid = (int)std::min<long>(nitems, num_sms());
+  timing_begin("tc_chol_update", st);
+  tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, a);
+  timing_end(st);
+  count_launch();
+  return check_launch("tc_chol_update");
+}
+
+// ---------------------------------------------------------------------------------- tensor-core triangular inverse
+// Row block K of X = L^-1:  X_KK = W_KK;  X[K, 0:K*128] = -(W_KK L[K, 0:K*128]) X[0:K*128, 0:K*128].
+// Lt = W_KK * L[K, 0:K*128] (SIMT, 128 x K*128), written as tf32 hi/lo [S][128][ld]
+__global__ void __launch_bounds__(256, 2) trtri_lt_kernel(int Npad, int K, const float* __restrict__ L,
+                                                           const float* __restrict__ winv, float* __restrict__ lthi,
+                                                           float* __restrict__ ltlo) {
+  using C = Cfg<float>;
+  constexpr int NB = C::NB, TM = C::TM, TN = C::TN;
+  __shared__ TileSmem<float> sm;
+  const int nblk = Npad / NB, J = blockIdx.x, s = blockIdx.y;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const float* W = winv + ((long)s * nblk + K) * NB * NB;
+  const float* Lk = L + (long)s * Npad * Npad + (long)K * NB * Npad + (long)J * NB;   // B(col c, k) = Lk[k*Npad + c]
+  float acc[TM][TN];
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
+  TileGemm<float, Lay::KContig, Lay::MContig, false>::run(acc, W, NB, Lk, Npad, NB, sm);
+  const long off = (long)s * NB * Npad + (long)J * NB;
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int g = 0; g < TN / 4; ++g) {
+      V4<float> h, l;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x = acc[r][g * 4 + e];
+        h.v[e] = tf32_hi(x);
+        l.v[e] = x - h.v[e];
+      }
+      const long o = off + (long)tile_row(ty, r) * Npad + g * 64 + tx * 4;
+      st4(lthi + o, h);
+      st4(ltlo + o, l);
+    }
+}
+
+// X_KK = W_KK and its transpose into X / X^T (hi, lo)
+__global__ void trtri_diag_store_kernel(int Npad, int Np, int K, const float* __restrict__ winv, float* __restrict__ xhi,
+                                        float* __restrict__ xlo, float* __restrict__ xthi, float* __restrict__ xtlo) {
+  constexpr int NB = 128;
+  const int s = blockIdx.y, nblk = Npad / NB;
+  const float* W = winv + ((long)s * nblk + K) * NB * NB;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NB * NB; e += gridDim.x * blockDim.x) {
+    int i = e / NB, k = e % NB;
+    float x = W[e], h = tf32_hi(x), l = x - h;
+    long o = ((long)s * Np + (long)K * NB + i) * Np + (long)K * NB + k;
+    long ot = ((long)s * Np + (long)K * NB + k) * Np + (long)K * NB + i;
+    xhi[o] = h; xlo[o] = l; xthi[ot] = h; xtlo[ot] = l;
+  }
+}
+
+size_t trtri_tc_workspace_bytes(int Npad, int Np, int S) {
+  return (2 * (size_t)S * Np * Np + 2 * (size_t)S * 128 * Npad) * sizeof(float);     // X^T hi|lo, Lt hi|lo
+}
+
+int trtri_split_tc(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi, float* linv_lo,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (Npad <= 0 || Npad % kNpadMult) return -1;
+  if (Np < Npad || Np % tc::BN) return -2;
+  if (S <= 0) return -3;
+  if (!L || !winv || !linv_hi || !linv_lo) return -4;
+  if (!workspace || workspace_bytes < trtri_tc_workspace_bytes(Npad, Np, S)) return -8;
+  float* xthi = reinterpret_cast<float*>(workspace);
+  float* xtlo = xthi + (size_t)S * Np * Np;
+  float* lthi = xtlo + (size_t)S * Np * Np;
+  float* ltlo = lthi + (size_t)S * 128 * Npad;
+  const size_t xb = (size_t)S * Np * Np * sizeof(float);
+  cudaMemsetAsync(linv_hi, 0, xb, st);
+  cudaMemsetAsync(linv_lo, 0, xb, st);
+  cudaMemsetAsync(xthi, 0, 2 * xb, st);
+  CUtensorMap mAhi, mAlo, mBhi, mBlo;
+  if (tc::make_map(&mAhi, lthi, (uint64_t)S * 128, Npad, tc::BM) || tc::make_map(&mAlo, ltlo, (uint64_t)S * 128, Npad, tc::BM) ||
+      tc::make_map(&mBhi, xthi, (uint64_t)S * Np, Np, tc::BN) || tc::make_map(&mBlo, xtlo, (uint64_t)S * Np, Np, tc::BN))
+    return 1999;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc::predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    attr = true;
+  }
+  const int nblk = Npad / 128;
+  timing_begin("trtri_kernel", st);
+  for (int K = 0; K < nblk; ++K) {
+    trtri_diag_store_kernel<<<dim3(8, S), 256, 0, st>>>(Npad, Np, K, winv, linv_hi, linv_lo, xthi, xtlo);
+    count_launch();
+    if (K == 0) continue;
+    trtri_lt_kernel<<<dim3(K, S), 256, 0, st>>>(Npad, K, L, winv, lthi, ltlo);
+    tc::Args a;
+    tc_args_init(a);
+    a.mode = 3; a.S = S; a.Np = Np; a.Npad = Npad; a.K = K;
+    a.ntiles = (K * 128 + tc::BN - 1) / tc::BN; a.npairs = 1; a.ngroups = 1;
+    a.xhi = linv_hi; a.xlo = linv_lo; a.xthi = xthi; a.xtlo = xtlo;
+    long nitems = (long)S * a.ntiles;
+    int grid = (int)std::min<long>(nitems, num_sms());
+    tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, a);
+    count_launch(2);
+  }
+  timing_end(st);
+  return check_launch("trtri_split_tc");
 }
 
 int linv_alpha(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y, const float* mean,
@@ -731,6 +934,8 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
     a.partial = partial; a.dbg = dbg;
     a.rect = 0; a.F = 0; a.M = M; a.c_begin = c_begin; a.ldm = ldm; a.mean = mean; a.mu_f = nullptr;
+    a.mode = 0; a.Npad = 0; a.jb = 0; a.ncols = 0; a.Cmat = nullptr; a.K = 0;
+    a.xhi = a.xlo = a.xthi = a.xtlo = nullptr;
     long nitems = (long)S * a.ntiles * npairs;
     int grid = (int)std::min<long>(nitems, num_sms());
     timing_begin("predict_tc_kernel", st);
@@ -741,7 +946,7 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     count_launch(3);
     if (fant) {      // fantasy means: same Kxt chunk against alpha^T, rectangular k range (OPT:609)
       tc::Args r = a;
-      r.rect = 1; r.F = F; r.mu_f = mu_f; r.ngroups = Fp / tc::BN; r.npairs = r.ngroups;
+      r.rect = 1; r.mode = 1; r.F = F; r.mu_f = mu_f; r.ngroups = Fp / tc::BN; r.npairs = r.ngroups;
       long nit = (long)S * r.ntiles * r.npairs;
       int gr = (int)std::min<long>(nit, num_sms());
       timing_begin("predict_tc_kernel_rect", st);

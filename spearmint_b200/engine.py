@@ -71,8 +71,14 @@ class Factor(object):
         st = eng.stream()
         check(fn("smk_cov_build", dt)(KINDS[kind], self.N, self.N, self.D, S, ptr(X), None, ptr(hb.inv_ls),
                                       ptr(hb.amp2), ptr(hb.noise), ptr(self.L), self.Npad, st), "cov_build")
-        check(fn("smk_potrf_lower_batched", dt)(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info), st),
-              "potrf")
+        if eng.factor_impl == "tc" and dt == torch.float32 and self.Npad >= 256:
+            nb = 2 * S * self.Npad * self.Npad * 4
+            ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+            check(_lib.lib().smk_potrf_lower_batched_tc_f32(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info),
+                                                            ptr(ws), nb, st), "potrf_tc")
+        else:
+            check(fn("smk_potrf_lower_batched", dt)(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info), st),
+                  "potrf")
 
     def linv(self):
         """(hi, lo, Np): explicit inverse of the factor split for the 3xTF32 tensor-core predict; computed once."""
@@ -82,10 +88,16 @@ class Factor(object):
             Np = L.smk_tc_np(self.N)
             hi = torch.empty((S, Np, Np), dtype=torch.float32, device=eng.device)
             lo = torch.empty((S, Np, Np), dtype=torch.float32, device=eng.device)
-            nb = L.smk_trtri_workspace_bytes(Np, S)
-            ws = torch.empty((nb,), dtype=torch.uint8, device=eng.device)
-            check(L.smk_trtri_split_f32(self.Npad, Np, S, ptr(self.L), ptr(self.winv), ptr(hi), ptr(lo), ptr(ws), nb,
-                                        eng.stream()), "trtri_split")
+            if eng.factor_impl == "tc" and self.Npad >= 256:
+                nb = L.smk_trtri_tc_workspace_bytes(self.Npad, Np, S)
+                ws = torch.empty((nb,), dtype=torch.uint8, device=eng.device)
+                check(L.smk_trtri_split_tc_f32(self.Npad, Np, S, ptr(self.L), ptr(self.winv), ptr(hi), ptr(lo), ptr(ws),
+                                               nb, eng.stream()), "trtri_split_tc")
+            else:
+                nb = L.smk_trtri_workspace_bytes(Np, S)
+                ws = torch.empty((nb,), dtype=torch.uint8, device=eng.device)
+                check(L.smk_trtri_split_f32(self.Npad, Np, S, ptr(self.L), ptr(self.winv), ptr(hi), ptr(lo), ptr(ws),
+                                            nb, eng.stream()), "trtri_split")
             self._linv = (hi, lo, Np)
         return self._linv
 
@@ -157,6 +169,8 @@ class GPEIEngine(object):
         self.predict_impl = os.environ.get("SMK_PREDICT_IMPL", "tc" if dtype == torch.float32 else "simt")
         if dtype != torch.float32:
             self.predict_impl = "simt"
+        # N^3 steps (Cholesky trailing update, triangular inverse): "tc" = tcgen05 3xTF32 left-looking variants
+        self.factor_impl = os.environ.get("SMK_FACTOR_IMPL", "tc" if self.predict_impl == "tc" else "simt")
         self.last = {}
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
 

@@ -84,3 +84,24 @@ def test_c_abi_host_entry_point():
     assert rc == 0 and np.all(info == 0)
     _check(out.T, g["overall_ei"], "f32")
     assert _lib.lib().smk_launch_count() > 0
+
+
+@pytest.mark.parametrize("D,N,M", [(4, 600, 700), (8, 1000, 900), (20, 1300, 600)])
+def test_ei_path_medium_n_vs_oracle(engines, D, N, M):
+    """The golden fixtures stop at N = 64 (one factor block).  These sizes run the whole tensor-core chain --
+    left-looking tcgen05 Cholesky (odd and even block counts), tcgen05 triangular inverse, 3xTF32 predict -- against
+    the float64 oracle with the same stated tolerance (|dEI| <= 5e-3 max EI, equal argmax unless the top-2 gap is inside it).
+    D=4 / N=600 is deliberately ill-conditioned (cond(K) ~ 1e6)."""
+    from oracle import gp_oracle as O
+    rs = np.random.RandomState(100 + D)
+    comp, cand = rs.rand(N, D), rs.rand(M, D)
+    cand[:10] = comp[0] + 1e-3 * rs.randn(10, D)            # the jitter cloud around an observed point (OPT:236-238)
+    y = np.sin(3 * comp).sum(1) + 0.01 * rs.randn(N)
+    vals = (y - y.mean()) / y.std()
+    hs = [(0.05 * rs.randn(), 1e-3, float(np.exp(0.25 * rs.randn())), rs.uniform(0.3, 2.0, D)) for _ in range(2)]
+    pend = np.zeros((0, D))
+    ref = O.ei_over_hypers("Matern52", hs, comp, pend, cand, vals)
+    eng = engines["f32"]
+    assert eng.predict_impl == "tc" and eng.factor_impl == "tc"
+    ei = eng.ei_over_hypers("Matern52", hs, comp, pend, cand, vals)
+    _check(ei, ref, "f32")
