@@ -208,7 +208,7 @@ def run_b200_arm(args, D, N, M, S):
             _, ei_sum, _ = eng.ei_over_hypers_device(KIND, hs_local, None, None, None, None, want_matrix=False,
                                                      inputs_on_device=res)
         else:
-            ei_sum = torch.zeros((ldm,), dtype=torch.float32, device=eng.device)
+            ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
         parallel.allreduce_sum_(ei_sum)
         idx, _ = eng.topk(ei_sum, M, 1)
         return idx
@@ -219,7 +219,7 @@ def run_b200_arm(args, D, N, M, S):
             ei, ei_sum, _ = eng.ei_over_hypers_device(KIND, hs_local, comp, None, cand, vals, want_matrix=True)
             host = ei[:, :M].t().contiguous().cpu()
         else:
-            ei_sum = torch.zeros((ldm,), dtype=torch.float32, device=eng.device)
+            ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
             host = None
         parallel.allreduce_sum_(ei_sum)
         idx, _ = eng.topk(ei_sum, M, 1)
@@ -284,7 +284,7 @@ def run_b200_arm(args, D, N, M, S):
     e2e_ms = wall_ms / max(1, min(args.steps, 3))
     esz = 4
     h2d = esz * (comp.size + cand.size + vals.size) + esz * Sl * (D + 3)
-    d2h = esz * (M * Sl + 1)
+    d2h = 8 * M * Sl + 4       # the (M, S_local) EI matrix is float64 (tail values), + the argmax index
 
     if rank == 0:
         pk = peaks()

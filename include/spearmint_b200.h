@@ -157,9 +157,11 @@ int smk_cross_mean_f64(int kind, int N, int Npad, int M, int D, int S, int F, co
  * mu: [S][F][ldm], var: [S][ldm], best: [S][F] (the caller fills min(vals) or the per-fantasy
  * bests, OPT:532 / OPT:597).  EI is evaluated in double, averaged over the F fantasies.
  * log_time (optional, [S][ldm]): EI is divided by exp(log_time) (PSEC:459, 490).
- * ei (optional): [S][ldm] per-sample EI;  ei_sum (optional): [ldm] += sum over s (caller zeroes). */
+ * ei (optional): [S][ldm] per-sample EI;  ei_sum (optional): [ldm] += sum over s (caller zeroes).
+ * ei and ei_sum are DOUBLE for both variants: late in a run max EI can be < 1e-38 and float storage would flush
+ * every candidate to zero (the reference ranks those tail values in float64).                              */
 int smk_ei_sweep_f32(int M, int S, int F, const float* mu, const float* var, int ldm,
-                     const float* best, const float* log_time, float* ei, float* ei_sum,
+                     const float* best, const float* log_time, double* ei, double* ei_sum,
                      void* stream);
 int smk_ei_sweep_f64(int M, int S, int F, const double* mu, const double* var, int ldm,
                      const double* best, const double* log_time, double* ei, double* ei_sum,

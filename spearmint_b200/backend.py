@@ -69,7 +69,7 @@ class DeviceBackend(object):
         eng = self.eng32
         ldm = _ceil(cand.shape[0], 128)
         if not st.hs:
-            return None, torch.zeros((ldm,), dtype=eng.dtype, device=eng.device)
+            return None, torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
         if st.preps is not None:
             return eng.ei_prepared(st.preps, eng.to_dev(cand), want_matrix, None)
         comp, pend, vals, normals, durs_log = st.args
@@ -83,7 +83,7 @@ class DeviceBackend(object):
         rank, world = parallel.world()
         if world == 1:
             return ei[:, :M].t().contiguous().double().cpu().numpy()
-        full = torch.zeros((st.S, _ceil(M, 128)), dtype=self.eng32.dtype, device=self.eng32.device)
+        full = torch.zeros((st.S, _ceil(M, 128)), dtype=torch.float64, device=self.eng32.device)
         if ei is not None:
             full[st.mine] = ei
         parallel.allreduce_sum_(full)                # columns are disjoint across ranks

@@ -60,7 +60,7 @@ template <typename T>
 int cross_mean(int, int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, T*,
                int, cudaStream_t);
 template <typename T>
-int ei_sweep(int, int, int, const T*, const T*, int, const T*, const T*, T*, T*, cudaStream_t);
+int ei_sweep(int, int, int, const T*, const T*, int, const T*, const T*, double*, double*, cudaStream_t);
 template <typename T>
 int topk(int, int, const T*, int*, T*, void*, size_t, cudaStream_t);
 template <typename T>
@@ -213,7 +213,7 @@ int smk_cross_mean_f64(int kind, int N, int Npad, int M, int D, int S, int F, co
 }
 
 int smk_ei_sweep_f32(int M, int S, int F, const float* mu, const float* var, int ldm, const float* best,
-                     const float* log_time, float* ei, float* ei_sum, void* stream) {
+                     const float* log_time, double* ei, double* ei_sum, void* stream) {
   return ei_sweep<float>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ST(stream));
 }
 int smk_ei_sweep_f64(int M, int S, int F, const double* mu, const double* var, int ldm, const double* best,
@@ -297,7 +297,7 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   float* winv = (float*)g_winv.get((size_t)S * Npad * NB * sizeof(float));
   float* alpha = (float*)g_alpha.get((size_t)S * Npad * sizeof(float));
   float* mv = (float*)g_mv.get(2 * (size_t)S * ldm * sizeof(float));
-  float* ei = (float*)g_ei.get((size_t)S * ldm * sizeof(float) + S * sizeof(int));
+  double* ei = (double*)g_ei.get((size_t)S * ldm * sizeof(double) + S * sizeof(int));
   const size_t wsb = smk_predict_tc_workspace_bytes(Np, M, S, 1);
   void* ws = g_ws.get(wsb);
   const size_t ws2b = smk_trtri_workspace_bytes(Np, S) + (size_t)S * Np * sizeof(float);
@@ -324,9 +324,9 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
                                mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, st)))
     return rc;
   if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, st))) return rc;
-  std::vector<float> hout((size_t)S * ldm);
+  std::vector<double> hout((size_t)S * ldm);
   std::vector<int> hinfo(S);
-  cudaMemcpyAsync(hout.data(), ei, hout.size() * sizeof(float), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hout.data(), ei, hout.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(hinfo.data(), info, S * sizeof(int), cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
@@ -337,7 +337,7 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   for (int s = 0; s < S; ++s) {
     if (info_out) info_out[s] = hinfo[s];
     if (hinfo[s]) bad = 1;
-    for (int j = 0; j < M; ++j) ei_out[(size_t)s * M + j] = (double)hout[(size_t)s * ldm + j];
+    for (int j = 0; j < M; ++j) ei_out[(size_t)s * M + j] = hout[(size_t)s * ldm + j];
   }
   return bad ? SMK_ERR_NOT_PD : SMK_OK;
 }

@@ -22,11 +22,14 @@ __device__ __forceinline__ double ei_one(double best, double m, double v) {
   return s * (u * cdf + pdf);
 }
 
+// EI values leave the kernel as DOUBLE for both element types: in the deep-tail regime (late in a run max EI can be
+// 1e-50 and smaller) float32 storage flushes every candidate to zero and the argmax degenerates, while the reference
+// ranks those values in float64.
 template <typename T>
 __global__ void __launch_bounds__(256) ei_sweep_kernel(int M, int S, int F, const T* __restrict__ mu,
                                                         const T* __restrict__ var, int ldm,
                                                         const T* __restrict__ best, const T* __restrict__ log_time,
-                                                        T* __restrict__ ei, T* __restrict__ ei_sum) {
+                                                        double* __restrict__ ei, double* __restrict__ ei_sum) {
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= M) return;
   double total = 0.0;
@@ -44,14 +47,14 @@ __global__ void __launch_bounds__(256) ei_sweep_kernel(int M, int S, int F, cons
       for (int q = 0; q < 4; ++q) {
         double e = ei_one((double)best[s + q], (double)m[q], (double)v[q]);
         if (log_time) e /= exp((double)lt[q]);
-        if (ei) ei[(long)(s + q) * ldm + j] = (T)e;
+        if (ei) ei[(long)(s + q) * ldm + j] = e;
         total += e;
       }
     }
     for (; s < S; ++s) {
       double e = ei_one((double)best[s], (double)mu[(long)s * ldm + j], (double)var[(long)s * ldm + j]);
       if (log_time) e /= exp((double)log_time[(long)s * ldm + j]);
-      if (ei) ei[(long)s * ldm + j] = (T)e;
+      if (ei) ei[(long)s * ldm + j] = e;
       total += e;
     }
   } else {
@@ -71,16 +74,16 @@ __global__ void __launch_bounds__(256) ei_sweep_kernel(int M, int S, int F, cons
       for (; f < F; ++f) acc += ei_one((double)brow[f], (double)mrow[(long)f * ldm], v);
       double e = acc / (double)F;
       if (log_time) e /= exp((double)log_time[(long)s * ldm + j]);
-      if (ei) ei[(long)s * ldm + j] = (T)e;
+      if (ei) ei[(long)s * ldm + j] = e;
       total += e;
     }
   }
-  if (ei_sum) ei_sum[j] += (T)total;
+  if (ei_sum) ei_sum[j] += total;
 }
 
 template <typename T>
-int ei_sweep(int M, int S, int F, const T* mu, const T* var, int ldm, const T* best, const T* log_time, T* ei,
-             T* ei_sum, cudaStream_t st) {
+int ei_sweep(int M, int S, int F, const T* mu, const T* var, int ldm, const T* best, const T* log_time, double* ei,
+             double* ei_sum, cudaStream_t st) {
   if (M <= 0) return -1;
   if (S <= 0) return -2;
   if (F <= 0) return -3;
@@ -93,8 +96,8 @@ int ei_sweep(int M, int S, int F, const T* mu, const T* var, int ldm, const T* b
   return check_launch("ei_sweep");
 }
 
-template int ei_sweep<float>(int, int, int, const float*, const float*, int, const float*, const float*, float*,
-                             float*, cudaStream_t);
+template int ei_sweep<float>(int, int, int, const float*, const float*, int, const float*, const float*, double*,
+                             double*, cudaStream_t);
 template int ei_sweep<double>(int, int, int, const double*, const double*, int, const double*, const double*,
                               double*, double*, cudaStream_t);
 

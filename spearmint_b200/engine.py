@@ -279,16 +279,16 @@ class GPEIEngine(object):
 
     def ei_sweep(self, M, S, F, mu, var, ldm, best, log_time=None, want_ei=True, ei_sum=None):
         dt = self.dtype
-        ei = torch.empty((S, ldm), dtype=dt, device=self.device) if want_ei else None
+        ei = torch.empty((S, ldm), dtype=torch.float64, device=self.device) if want_ei else None   # EI is always double
         if ei_sum is None:
-            ei_sum = torch.zeros((ldm,), dtype=dt, device=self.device)
+            ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=self.device)
         check(fn("smk_ei_sweep", dt)(M, S, F, ptr(mu), ptr(var), ldm, ptr(best), ptr(log_time), ptr(ei),
                                      ptr(ei_sum), self.stream()), "ei_sweep")
         return ei, ei_sum
 
     def topk(self, score, M, k):
         """Indices of the k largest scores, ascending (argsort(score)[-k:], OPT:270; [-1] is the argmax, OPT:294)."""
-        dt = self.dtype
+        dt = score.dtype                      # EI scores are float64 (see ei_sweep)
         nb = _lib.lib().smk_topk_workspace_bytes(M, k)
         ws = torch.empty((nb,), dtype=torch.uint8, device=self.device)
         idx = torch.empty((k,), dtype=torch.int32, device=self.device)
@@ -412,8 +412,8 @@ class GPEIEngine(object):
         ldm = _ceil(M, 128)
         Fn = 1 if P == 0 else int(normals.shape[-1])
         chunk = self.max_samples_per_chunk(_ceil(N + P, 128), ldm, Fn)
-        ei_sum = torch.zeros((ldm,), dtype=self.dtype, device=self.device)
-        ei_all = torch.empty((S, ldm), dtype=self.dtype, device=self.device) if want_matrix else None
+        ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=self.device)
+        ei_all = torch.empty((S, ldm), dtype=torch.float64, device=self.device) if want_matrix else None
         for s0 in range(0, S, chunk):
             r = res if (res is not None and chunk >= S) else (dict(res, hb=None) if res is not None else None)
             nrm = normals[s0:s0 + chunk] if (normals is not None and np.ndim(normals) == 3) else normals
