@@ -323,10 +323,10 @@ class GPEIEngine(object):
             self._t1("cov_potrf", t)
             t = self._t0()
             if self.predict_impl == "tc":
-                alpha = fac.alpha_via_linv(yd)       # two parallel mat-vecs with the explicit inverse
+                alpha = fac.alpha_via_linv(yd)       # explicit inverse (trtri, once per factor batch) + two mat-vecs
             else:
                 alpha, _, _ = fac.solve(yd, F=1)
-            self._t1("chol_solve", t)
+            self._t1("linv_alpha" if self.predict_impl == "tc" else "chol_solve", t)
             p.fac, p.alpha, p.F = fac, alpha, 1
             p.bests = torch.full((hb.S, 1), best_val, dtype=self.dtype, device=self.device)
             p.bests_host = np.full((hb.S, 1), best_val)
