@@ -183,15 +183,31 @@ __global__ void alpha_split_kernel(int N, int Np, int F, int Fp, int Npad_alpha,
 
 // ================================================================================================= kxt (SIMT)
 // One block = 128 candidates x all n in tiles of 128, 8x8 register micro-tiles (rows = candidates, cols = n):
-// Kxt[s][c][n] as (hi, lo) float4 stores (256 B contiguous per 16 threads), mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.
-// grid = (Mc/128, S).  Output-bound: 8 B written per (3D + 25) flops.
+// Kxt[s][c][n] as float4 stores (256 B contiguous per 16 threads), mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.
+// grid = (Mc/128, S).  4 B written per (3D + 25) flops.
+// Fast stationary kernels for the generator (float32): r = r2 * rsqrt(r2) and exp(x) = ex2.approx(x * log2 e), each ~2 ulp.
+// Their relative error (~2e-7) is below the tf32 hi/lo representation error of the operand (2^-21 = 4.8e-7) that
+// follows; the accurate sqrtf/expf versions cost ~25 of the ~110 instructions per element of this instruction-bound kernel.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float kernel_of_r2_fast(int kind, float r2) {
+  if (kind <= 1) return fast_exp(-0.5f * r2);
+  float r = (r2 > 0.f) ? r2 * rsqrtf(r2) : 0.f;
+  if (kind == 2) { float a = 1.7320508075688772f * r; return (1.f + a) * fast_exp(-a); }
+  float a = 2.23606797749979f * r;
+  return (1.f + a + (5.0f / 3.0f) * r2) * fast_exp(-a);
+}
+
 constexpr int kKD = 16;   // D chunk staged in shared memory (17 KB total: co-resides with the 198 KB MMA block)
 
 __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, int M, int c_begin, int Mc, int D,
                                                      const float* __restrict__ X, const float* __restrict__ Cc,
                                                      const float* __restrict__ inv_ls, const float* __restrict__ amp2,
                                                      const float* __restrict__ mean, const float* __restrict__ alpha,
-                                                     int Npad_alpha, float* __restrict__ khi, float* __restrict__ klo,
+                                                     int Npad_alpha, float* __restrict__ kout,
                                                      float* __restrict__ mu, int ldm) {
   constexpr int T = 128, LDT = T + kPad;
   __shared__ __align__(16) float stage[2][kKD][LDT];
@@ -251,22 +267,19 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      float* oh = khi + ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
-      float* ol = klo + ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
+      float* ok = kout + ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        V4<float> h, l;
+        V4<float> kv4;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = g * 4 + e;
           const int n = n0 + g * 64 + tx * 4 + e;
-          float kv = (n < N) ? a2 * kernel_of_r2<float>(kind, acc[r][c]) : 0.f;
+          float kv = (n < N) ? a2 * kernel_of_r2_fast(kind, acc[r][c]) : 0.f;
           mdot[r] = fmaf(av[c], kv, mdot[r]);
-          h.v[e] = tf32_hi(kv);
-          l.v[e] = kv - h.v[e];
+          kv4.v[e] = kv;
         }
-        st4(oh + g * 64 + tx * 4, h);
-        st4(ol + g * 64 + tx * 4, l);
+        st4(ok + g * 64 + tx * 4, kv4);      // plain float32: the tf32 hi/lo pair is formed inside the MMA kernel
       }
     }
   }
@@ -295,7 +308,7 @@ static_assert(ROW_BYTES == 64 || ROW_BYTES == 128, "operand rows must be one 64B
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 constexpr int B_BYTES = BN * BK * 4;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
-constexpr int THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int THREADS = 320;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue, warps 6-9: operand splitter
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -377,6 +390,8 @@ struct Args {
   // mode 2 (left-looking Cholesky update, potrf_tc): C[(jb+m)-th block row][block cols jb, jb+1] -= L[.., 0:jb] L[jb.., 0:jb]^T
   // mode 3 (triangular inverse, row block K): X[K, 0:K*128] = -Lt * X[0:K*128, 0:K*128], stored as X and X^T, hi/lo
   int mode;            // 0 tri (predict), 1 rect (fantasy means), 2 Cholesky update, 3 trtri row block
+  int a_raw;           // 1: the A operand arrives as plain float32 (map mAhi) and is split into tf32 hi/lo in shared
+                       //    memory by the splitter warps; 0: A arrives pre-split (maps mAhi, mAlo)
   int Npad, jb, ncols; // mode 2: factor leading dimension, first block column of the pair, valid columns (128 | 256)
   float* Cmat;         // mode 2: [S][Npad][Npad] matrix being factored
   int K;               // mode 3: row block
@@ -428,15 +443,16 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   // 1024-byte alignment required by the 128B swizzle atoms
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                 // [STAGES]
-  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* full = bars;                 // [STAGES]  operands ready for the MMA (arrived by the 4 splitter warps)
+  uint64_t* empty = bars + STAGES;       // [STAGES]  stage consumed (tcgen05.commit)
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rawf = tempty + 2;           // [STAGES]  TMA bytes landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rawf + STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); mbar_init(&rawf[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -467,11 +483,11 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* sb = base + stage * STAGE_BYTES;
             const int kk = it.k0 + kc * BK;
-            mbar_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(&mAhi, &full[stage], sb, kk, it.rowA, hintA);
-            tma_load_2d(&mAlo, &full[stage], sb + A_BYTES, kk, it.rowA, hintA);
-            tma_load_2d(&mBhi, &full[stage], sb + 2 * A_BYTES, kk, it.rowB, hintB);
-            tma_load_2d(&mBlo, &full[stage], sb + 2 * A_BYTES + B_BYTES, kk, it.rowB, hintB);
+            mbar_expect_tx(&rawf[stage], p.a_raw ? (A_BYTES + 2 * B_BYTES) : STAGE_BYTES);
+            tma_load_2d(&mAhi, &rawf[stage], sb, kk, it.rowA, hintA);
+            if (!p.a_raw) tma_load_2d(&mAlo, &rawf[stage], sb + A_BYTES, kk, it.rowA, hintA);
+            tma_load_2d(&mBhi, &rawf[stage], sb + 2 * A_BYTES, kk, it.rowB, hintB);
+            tma_load_2d(&mBlo, &rawf[stage], sb + 2 * A_BYTES + B_BYTES, kk, it.rowB, hintB);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -507,6 +523,41 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           umma_commit(&tfull[buf]);
           buf ^= 1;
           if (buf == 0) bphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // splitter warps: once the TMA bytes of a stage have landed, turn the float32 A tile into its tf32 (hi, lo) pair in
+    // place (hi = x & 0xffffe000 stays in the A slot, lo = x - hi goes to the A_lo slot), make the generic-proxy writes
+    // visible to the async proxy (tcgen05.mma reads shared memory through it) and release the stage to the MMA warp.
+    // The operation is elementwise on raw bytes, so it is oblivious to the swizzled layout.
+    const int ts = threadIdx.x - 192;       // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
+      for (int h = 0; h < 2; ++h) {
+        const Item it = get_item(p, w, h);
+        if (!it.valid) break;
+        for (int kc = 0; kc < it.nk; ++kc) {
+          mbar_wait(&rawf[stage], phase);
+          if (p.a_raw) {
+            float4* a = reinterpret_cast<float4*>(base + stage * STAGE_BYTES);
+            float4* l = reinterpret_cast<float4*>(base + stage * STAGE_BYTES + A_BYTES);
+#pragma unroll
+            for (int q = 0; q < A_BYTES / 16 / 128; ++q) {
+              float4 x = a[ts + q * 128], hh, ll;
+              hh.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); ll.x = x.x - hh.x;
+              hh.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); ll.y = x.y - hh.y;
+              hh.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); ll.z = x.z - hh.z;
+              hh.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); ll.w = x.w - hh.w;
+              a[ts + q * 128] = hh;
+              l[ts + q * 128] = ll;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -827,7 +878,7 @@ static bool tc_overlap_enabled() {
 }
 // workspace: Kxt hi | Kxt lo | partial
 static size_t tc_chunk_cands(int Np, int M, int S, size_t budget) {
-  size_t per_cand = 2 * (size_t)S * Np * sizeof(float);
+  size_t per_cand = (size_t)S * Np * sizeof(float);
   size_t mpad = ((size_t)M + 127) / 128 * 128;
   size_t mc = budget / per_cand;
   if (mc >= mpad) return mpad;                  // everything in one chunk: single buffer
@@ -848,7 +899,7 @@ static int fant_rows(int F) { return F > 1 ? ((F + tc::BN - 1) / tc::BN) * tc::B
 size_t predict_tc_workspace_bytes(int Np, int M, int S, int F) {
   size_t mc = tc_chunk_cands(Np, M, S, kTcBudget);
   int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2, nbuf = tc_nbuf(Np, M, S, kTcBudget);
-  return (size_t)nbuf * 2 * S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) +
+  return (size_t)nbuf * S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) +
          2 * (size_t)S * fant_rows(F) * Np * sizeof(float) + 1024;
 }
 
@@ -869,8 +920,8 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   const int Mc = (int)tc_chunk_cands(Np, M, S, kTcBudget);
   const int nbuf = tc_nbuf(Np, M, S, kTcBudget);
   const int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
-  float* khi = reinterpret_cast<float*>(workspace);                       // [nbuf][hi | lo][S][Mc][Np]
-  float* partial = khi + (size_t)nbuf * 2 * S * Mc * Np;
+  float* khi = reinterpret_cast<float*>(workspace);                       // [nbuf][S][Mc][Np] float32 cross-covariance
+  float* partial = khi + (size_t)nbuf * S * Mc * Np;
   const int Fp = fant ? fant_rows(F) : 0;
   float* ahi = partial + (size_t)npairs * S * Mc;               // alpha^T hi | lo  [S][Fp][Np]
   float* alo = ahi + (size_t)S * Fp * Np;
@@ -885,10 +936,9 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
 
   CUtensorMap mAhi[2], mAlo[2], mBhi, mBlo;
   for (int b = 0; b < nbuf; ++b) {
-    float* kh = khi + (size_t)b * 2 * S * Mc * Np;
-    if (tc::make_map(&mAhi[b], kh, (uint64_t)S * Mc, Np, tc::BM) ||
-        tc::make_map(&mAlo[b], kh + (size_t)S * Mc * Np, (uint64_t)S * Mc, Np, tc::BM))
-      return 1999;   // SMK_ERR_CUDA range: cuTensorMapEncodeTiled unavailable / failed
+    float* kh = khi + (size_t)b * S * Mc * Np;
+    if (tc::make_map(&mAhi[b], kh, (uint64_t)S * Mc, Np, tc::BM)) return 1999;   // cuTensorMapEncodeTiled failed
+    mAlo[b] = mAhi[b];                                                           // unused in a_raw mode
   }
   if (tc::make_map(&mBhi, linv_hi, (uint64_t)S * Np, Np, tc::BN) || tc::make_map(&mBlo, linv_lo, (uint64_t)S * Np, Np, tc::BN))
     return 1999;
@@ -918,13 +968,12 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   int ci = 0;
   for (int c_begin = 0; c_begin < M; c_begin += Mc, ++ci) {
     const int b = overlap ? (ci & 1) : 0;
-    float* kh = khi + (size_t)b * 2 * S * Mc * Np;
-    float* kl = kh + (size_t)S * Mc * Np;
+    float* kh = khi + (size_t)b * S * Mc * Np;
     const int mc_used = min(Mc, ((M - c_begin) + 127) / 128 * 128);
     if (overlap && ci >= 2) cudaStreamWaitEvent(aux, ev_mma[b], 0);      // buffer b is free again
     timing_begin("kxt_kernel", kst);
     kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, kst>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
-                                                        alpha, Npad_alpha, kh, kl, mu, ldm);
+                                                        alpha, Npad_alpha, kh, mu, ldm);
     timing_end(kst);
     if (overlap) {
       cudaEventRecord(ev_kxt[b], aux);
@@ -934,7 +983,7 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
     a.partial = partial; a.dbg = dbg;
     a.rect = 0; a.F = 0; a.M = M; a.c_begin = c_begin; a.ldm = ldm; a.mean = mean; a.mu_f = nullptr;
-    a.mode = 0; a.Npad = 0; a.jb = 0; a.ncols = 0; a.Cmat = nullptr; a.K = 0;
+    a.mode = 0; a.a_raw = 1; a.Npad = 0; a.jb = 0; a.ncols = 0; a.Cmat = nullptr; a.K = 0;
     a.xhi = a.xlo = a.xthi = a.xtlo = nullptr;
     long nitems = (long)S * a.ntiles * npairs;
     int grid = (int)std::min<long>(nitems, num_sms());

@@ -196,7 +196,7 @@ def test_topk_matches_numpy(engines, M, k):
 
 
 # ------------------------------------------------------------------------------------------------ tensor-core predict
-@pytest.mark.parametrize("D,N,M", [(6, 100, 128), (8, 300, 1000), (3, 520, 257)])
+@pytest.mark.parametrize("D,N,M", [(6, 100, 128), (8, 300, 1000), (3, 520, 257), (40, 260, 200)])
 def test_predict_tc_beta_and_moments(engines, D, N, M):
     """tcgen05 3xTF32 path: the dumped beta^T = Kx^T L^-T tile product (descriptor / swizzle / pipeline check) and
     the resulting moments, against the oracle."""
