@@ -274,7 +274,7 @@ def run_b200_arm(args, D, N, M, S):
 
     # kernel spans of the resident leg are read below; freeze them before the e2e leg runs
     span = {}
-    for nm in ("predict_tc_kernel", "predict_kernel", "kxt_kernel", "trtri_kernel"):
+    for nm in ("predict_tc_kernel", "predict_kernel", "kxt_kernel", "trtri_kernel", "linv_pack_f16"):
         c2 = ctypes.c_int(0)
         span[nm] = (L.smk_timing_ms(nm.encode(), ctypes.byref(c2)), c2.value)
 
@@ -299,18 +299,19 @@ def run_b200_arm(args, D, N, M, S):
         alg = (float(N) * N if impl == "tc" else flops_per_pair(N, D)) * pairs_local
         achieved = alg / (kms_step * 1e-3) / 1e12 if kms_step > 0 else None
         other = {}
-        for nm in ("kxt_kernel", "trtri_kernel"):
+        for nm in ("kxt_kernel", "trtri_kernel", "linv_pack_f16"):
             if span[nm][1]:
                 other[nm + "_ms_per_step"] = span[nm][0] / args.steps
-        roof = {"kernel": "smk::tc::predict_tc_kernel (tcgen05.mma kind::tf32, 3xTF32 split)" if impl == "tc"
+        roof = {"kernel": "smk::tc::predict_tc_kernel (tcgen05.mma kind::f16, 3xFP16 scaled split, fp32 accumulate)" if impl == "tc"
                 else "smk::predict_kernel<float> (SIMT FMA)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": (achieved / pk["tensor_sustained"]) if achieved else None, "traffic": None,
                 "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": alg / n_launch_step, "launches_per_step": n_launch_step,
                 "kernel_ms_per_launch": kms_step / n_launch_step, "kernel_ms_per_step": kms_step,
-                "note": "fp32-accurate results need 3 TF32 MMAs per product (hi*hi + hi*lo + lo*hi): 6 bf16-equivalent "
-                        "tensor flops per algorithmic flop, so 1/6 = 0.167 of the bf16 peak is this formulation's ceiling"
+                "note": "fp32-accurate results need 3 fp16 MMAs per product (hi*hi + hi*lo + lo*hi, operands scaled by exact "
+                        "powers of two): 3 bf16-equivalent tensor flops per algorithmic flop, so 1/3 = 0.333 of the "
+                        "bf16 peak is this formulation's ceiling"
                         if impl == "tc" else "float32 SIMT FMA path (B200 fp32 vector peak ~74 TFLOP/s)",
                 "stage_ms_per_step": dict({k: v / args.steps for k, v in stages.items()}, **other)}
         cpu = cpu_port_sample(D, N, M, S, budget_cands=args.cpu_cands) if world == 1 and not args.no_cpu else None

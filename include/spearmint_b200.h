@@ -109,11 +109,15 @@ int smk_predict_f64(int kind, int N, int Npad, int M, int D, int S, const double
                     const double* winv, const double* alpha, double* mu, double* var, int ldm,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- (4-tc) fused predict on the tensor cores (tcgen05 + TMEM + TMA, 3xTF32 split; float32 only)
- * Same outputs as smk_predict_f32 (OPT:536, 544, 547-548).  Two steps so that the factor-only part is done once:
- *   smk_trtri_split_f32 : Linv = L^-1 (explicit inverse of the blocked factor) split into tf32 hi / lo parts,
+/* ---- (4-tc) fused predict on the tensor cores (tcgen05 + TMEM + TMA; float32 in/out, 3 x FP16 split products
+ *      with exact power-of-two operand scaling, fp32 accumulation)
+ * Same outputs as smk_predict_f32 (OPT:536, 544, 547-548).  Steps, so that the factor-only part is done once:
+ *   smk_trtri_split_f32 : Linv = L^-1 (explicit inverse of the blocked factor) as a tf32 hi / lo pair of float arrays,
  *                         each [S][Np][Np] with Np = smk_tc_np(N) (N rounded up to 256), zero above the diagonal.
- *   smk_predict_tc_f32  : cross-covariance (candidate-major, split) -> D = Kxt * Linv^T on tcgen05 -> var, mu.
+ *   smk_linv_pack_f16   : the GEMM operand copy of Linv: per-sample scale 2^linv_exp[s] (largest |entry| -> [2^14, 2^15))
+ *                         and the round-to-nearest fp16 (hi, lo) pair, each [S][Np][Np] halves.
+ *                         linv_exp: [2*S] ints (first S: exponents, rest scratch).
+ *   smk_predict_tc_f32  : cross-covariance (candidate-major, fp16 hi/lo) -> D = Kxt * Linv^T on tcgen05 -> var, mu.
  * alpha: [S][Npad_alpha] (first right-hand side).  dbg_beta (tests only, may be NULL): [S][Mc][Np] dump of
  * beta^T for a single-chunk call.                                                                              */
 int smk_tc_np(int N);
@@ -136,11 +140,13 @@ int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* 
 size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F);
 /* F > 1 with alpha_f [S][F][Npad_alpha] and mu_f [S][F][ldm] non-NULL: additionally the fantasy means
  * mu_f[s][f][j] = cov(X, C_j)' alpha_f[s][f] + mean[s]  (OPT:609) as a second tcgen05 GEMM on the same Kxt chunk. */
+int smk_linv_pack_f16(int Np, int S, const float* linv_hi, const float* linv_lo, void* linv_h16, void* linv_l16,
+                      int* linv_exp, void* stream);
 int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
-                       const float* inv_ls, const float* amp2, const float* mean, const float* linv_hi,
-                       const float* linv_lo, const float* alpha, int Npad_alpha, float* mu, float* var, int ldm,
-                       void* workspace, size_t workspace_bytes, float* dbg_beta, int F, const float* alpha_f,
-                       float* mu_f, void* stream);
+                       const float* inv_ls, const float* amp2, const float* mean, const void* linv_h16,
+                       const void* linv_l16, const int* linv_exp, const float* alpha, int Npad_alpha, float* mu,
+                       float* var, int ldm, void* workspace, size_t workspace_bytes, float* dbg_beta, int F,
+                       const float* alpha_f, float* mu_f, void* stream);
 
 /* ---- (4b) cross mean only: mu[s][f][j] = cov(X, C_j)' alpha[s][f] + mean[s]
  *          time-GP mean of EI-per-second (PSEC:442-459) and fantasy means (OPT:609).

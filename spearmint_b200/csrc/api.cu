@@ -1,4 +1,5 @@
 // api.cu -- extern "C" surface of libspearmint_b200.so (see include/spearmint_b200.h).
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -75,9 +76,10 @@ int potrf_lower_batched_tc(int, int, float*, float*, int*, float*, float*, cudaS
 size_t trtri_tc_workspace_bytes(int, int, int);
 int trtri_split_tc(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
 int linv_alpha(int, int, int, const float*, const float*, const float*, const float*, float*, int, float*, cudaStream_t);
+int linv_pack_f16(int, int, const float*, const float*, __half*, __half*, int*, cudaStream_t);
 int predict_tc(int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
-               const float*, const float*, const float*, int, float*, float*, int, void*, size_t, float*, int,
-               const float*, float*, cudaStream_t);
+               const __half*, const __half*, const int*, const float*, int, float*, float*, int, void*, size_t, float*,
+               int, const float*, float*, cudaStream_t);
 size_t predict_workspace_bytes_any(int, int);
 
 }  // namespace smk
@@ -192,13 +194,19 @@ int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* 
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream) {
   return linv_alpha(N, Np, S, linv_hi, linv_lo, y, mean, alpha, ld_alpha, tmp, ST(stream));
 }
+int smk_linv_pack_f16(int Np, int S, const float* linv_hi, const float* linv_lo, void* linv_h16, void* linv_l16,
+                      int* linv_exp, void* stream) {
+  return linv_pack_f16(Np, S, linv_hi, linv_lo, reinterpret_cast<__half*>(linv_h16), reinterpret_cast<__half*>(linv_l16),
+                       linv_exp, ST(stream));
+}
 int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
-                       const float* inv_ls, const float* amp2, const float* mean, const float* linv_hi,
-                       const float* linv_lo, const float* alpha, int Npad_alpha, float* mu, float* var, int ldm,
-                       void* workspace, size_t workspace_bytes, float* dbg_beta, int F, const float* alpha_f,
-                       float* mu_f, void* stream) {
-  return predict_tc(kind, N, Np, M, D, S, X, C, inv_ls, amp2, mean, linv_hi, linv_lo, alpha, Npad_alpha, mu, var, ldm,
-                    workspace, workspace_bytes, dbg_beta, F, alpha_f, mu_f, ST(stream));
+                       const float* inv_ls, const float* amp2, const float* mean, const void* linv_h16,
+                       const void* linv_l16, const int* linv_exp, const float* alpha, int Npad_alpha, float* mu,
+                       float* var, int ldm, void* workspace, size_t workspace_bytes, float* dbg_beta, int F,
+                       const float* alpha_f, float* mu_f, void* stream) {
+  return predict_tc(kind, N, Np, M, D, S, X, C, inv_ls, amp2, mean, reinterpret_cast<const __half*>(linv_h16),
+                    reinterpret_cast<const __half*>(linv_l16), linv_exp, alpha, Npad_alpha, mu, var, ldm, workspace,
+                    workspace_bytes, dbg_beta, F, alpha_f, mu_f, ST(stream));
 }
 
 int smk_cross_mean_f32(int kind, int N, int Npad, int M, int D, int S, int F, const float* X, const float* C,
@@ -263,7 +271,7 @@ struct DevBuf {
     return p;
   }
 };
-DevBuf g_in, g_fac, g_winv, g_alpha, g_mv, g_ws, g_ei, g_linv, g_ws2;
+DevBuf g_in, g_fac, g_winv, g_alpha, g_mv, g_ws, g_ei, g_linv, g_ws2, g_l16;
 std::vector<float> g_host;
 }  // namespace
 
@@ -303,7 +311,8 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   const size_t ws2b = smk_trtri_workspace_bytes(Np, S) + (size_t)S * Np * sizeof(float);
   void* ws2 = g_ws2.get(ws2b);
   float* linv = (float*)g_linv.get(2 * (size_t)S * Np * Np * sizeof(float));
-  if (!d || !fac || !winv || !alpha || !mv || !ei || !ws || !ws2 || !linv) {
+  unsigned char* l16 = (unsigned char*)g_l16.get(2 * (size_t)S * Np * Np * sizeof(__half) + 2 * (size_t)S * sizeof(int));
+  if (!d || !fac || !winv || !alpha || !mv || !ei || !ws || !ws2 || !linv || !l16) {
     snprintf(g_err, sizeof(g_err), "cudaMalloc failed");
     return SMK_ERR_CUDA;
   }
@@ -314,13 +323,17 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   int rc;
   if ((rc = smk_cov_build_f32(kind, N, N, D, S, dX, nullptr, dil, da, dn, fac, Npad, st))) return rc;
   if ((rc = smk_potrf_lower_batched_f32(Npad, S, fac, winv, info, st))) return rc;
-  // tensor-core path: explicit inverse (split), alpha by two mat-vecs, tcgen05 3xTF32 predict
+  // tensor-core path: explicit inverse (split), alpha by two mat-vecs, fp16 operand pack, tcgen05 3xFP16 predict
   float* lhi = linv;
   float* llo = linv + (size_t)S * Np * Np;
   float* tmp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws2) + smk_trtri_workspace_bytes(Np, S));
   if ((rc = smk_trtri_split_f32(Npad, Np, S, fac, winv, lhi, llo, ws2, smk_trtri_workspace_bytes(Np, S), st))) return rc;
   if ((rc = smk_linv_alpha_f32(N, Np, S, lhi, llo, dy, dm, alpha, Npad, tmp, st))) return rc;
-  if ((rc = smk_predict_tc_f32(kind, N, Np, M, D, S, dX, dC, dil, da, dm, lhi, llo, alpha, Npad, mv,
+  void* lh16 = l16;
+  void* ll16 = l16 + (size_t)S * Np * Np * sizeof(__half);
+  int* lexp = reinterpret_cast<int*>(l16 + 2 * (size_t)S * Np * Np * sizeof(__half));
+  if ((rc = smk_linv_pack_f16(Np, S, lhi, llo, lh16, ll16, lexp, st))) return rc;
+  if ((rc = smk_predict_tc_f32(kind, N, Np, M, D, S, dX, dC, dil, da, dm, lh16, ll16, lexp, alpha, Npad, mv,
                                mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, st)))
     return rc;
   if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, st))) return rc;

@@ -15,6 +15,7 @@
 // Why 3xTF32: a single TF32 pass (10-bit mantissa) cannot resolve var = amp2 - |beta|^2 (it goes negative on the
 // reference's own test problems); hi/lo splitting restores ~2^-21 operand accuracy at 3 MMAs
 // per product, i.e. 1/6 of the dense bf16 tensor peak is the ceiling of this formulation.
+#include <cuda_fp16.h>
 #include <cuda.h>
 
 #include <algorithm>
@@ -167,27 +168,109 @@ __global__ void __launch_bounds__(256) linv_mtv_kernel(int N, int Np, int ld_alp
   if (ph == 0 && c < ld_alpha) alpha[(long)s * ld_alpha + c] = (c < N) ? red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl] : 0.f;
 }
 
-// alpha^T (hi, lo) for the rectangular fantasy-mean GEMM: out[s][f][n], f padded to Fp rows, n padded to Np (zeros)
-__global__ void alpha_split_kernel(int N, int Np, int F, int Fp, int Npad_alpha, long total,
-                                   const float* __restrict__ alpha, float* __restrict__ hi, float* __restrict__ lo) {
+// ---------------------------------------------------------------------------------------------- fp16 operand packing
+// The predict GEMMs run as 3 x FP16 tensor products (hi*hi + hi*lo + lo*hi, fp32 accumulate).  fp16 carries the same
+// 11-bit significand as tf32 at twice the tensor rate but only 5 exponent bits, so every operand matrix is multiplied
+// by an exact power of two that puts its largest |entry| in [2^14, 2^15) before the round-to-nearest split
+//     hi = fp16(x * 2^e),   lo = fp16(x * 2^e - hi)
+// (representation error <= 2^-23 |x| for entries within 2^-18 of the maximum, <= 2^-40 max|x| absolute below that;
+// tools/fp16_split_experiment.py, profiles/r01_fp16_split_experiment.md).  The epilogue multiplies the accumulator by
+// 2^-(ea + eb); the scaling is exact, so it changes nothing but the representable range.
+__host__ __device__ __forceinline__ int scale_exp(float amax) {
+  int e;
+  frexpf(amax * 1.00001f, &e);          // amax * 1.00001 < 2^e
+  return 15 - e;
+}
+__device__ __forceinline__ int kx_exp(float amp2) { return scale_exp(amp2 * 1.000001f); }   // cross-covariance <= amp2 (1 + 1e-6)
+__device__ __forceinline__ void split16(float x, __half& h, __half& l) {
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ uint2 pack4(const __half (&v)[4]) {
+  __half2 a = __halves2half2(v[0], v[1]), b = __halves2half2(v[2], v[3]);
+  uint2 r;
+  r.x = *reinterpret_cast<unsigned*>(&a);
+  r.y = *reinterpret_cast<unsigned*>(&b);
+  return r;
+}
+
+// max |hi + lo| per sample (bits of a non-negative float order like unsigned integers)
+__global__ void __launch_bounds__(256) linv_absmax_kernel(long per4, const float4* __restrict__ hi,
+                                                          const float4* __restrict__ lo, unsigned* __restrict__ maxbits) {
+  const int s = blockIdx.y;
+  const float4* h = hi + (long)s * per4;
+  const float4* l = lo + (long)s * per4;
+  float m = 0.f;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per4; e += (long)gridDim.x * blockDim.x) {
+    float4 a = h[e], b = l[e];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x + b.x), fabsf(a.y + b.y)), fmaxf(fabsf(a.z + b.z), fabsf(a.w + b.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&maxbits[s], __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(256) linv_pack_f16_kernel(long per4, const float4* __restrict__ hi,
+                                                            const float4* __restrict__ lo,
+                                                            const unsigned* __restrict__ maxbits, uint2* __restrict__ oh,
+                                                            uint2* __restrict__ ol, int* __restrict__ exps) {
+  const int s = blockIdx.y;
+  const int eb = scale_exp(__uint_as_float(maxbits[s]));
+  const float sc = ldexpf(1.f, eb);
+  if (blockIdx.x == 0 && threadIdx.x == 0) exps[s] = eb;
+  const long base = (long)s * per4;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per4; e += (long)gridDim.x * blockDim.x) {
+    float4 a = hi[base + e], b = lo[base + e];
+    __half hh[4], ll[4];
+    split16((a.x + b.x) * sc, hh[0], ll[0]);
+    split16((a.y + b.y) * sc, hh[1], ll[1]);
+    split16((a.z + b.z) * sc, hh[2], ll[2]);
+    split16((a.w + b.w) * sc, hh[3], ll[3]);
+    oh[base + e] = pack4(hh);
+    ol[base + e] = pack4(ll);
+  }
+}
+
+// alpha^T for the rectangular fantasy-mean GEMM, fp16 (hi, lo): out[s][f][n], f padded to Fp rows, n padded to Np
+// (zeros), scaled per sample by 2^fexp[s].  One block per sample finds the scale, then the elementwise pack.
+__global__ void __launch_bounds__(256) alpha_absmax_kernel(int N, int F, int Npad_alpha, const float* __restrict__ alpha,
+                                                           int* __restrict__ fexp) {
+  __shared__ float red[8];
+  const int s = blockIdx.x;
+  float m = 0.f;
+  for (long e = threadIdx.x; e < (long)F * N; e += blockDim.x) {
+    int f = (int)(e / N), n = (int)(e % N);
+    m = fmaxf(m, fabsf(alpha[((long)s * F + f) * Npad_alpha + n]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    fexp[s] = scale_exp(m);
+  }
+}
+__global__ void alpha_pack_f16_kernel(int N, int Np, int F, int Fp, int Npad_alpha, long total,
+                                      const float* __restrict__ alpha, const int* __restrict__ fexp,
+                                      __half* __restrict__ hi, __half* __restrict__ lo) {
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   int n = (int)(e % Np);
   long sf = e / Np;
   int f = (int)(sf % Fp), s = (int)(sf / Fp);
-  float x = (f < F && n < N) ? alpha[((long)s * F + f) * Npad_alpha + n] : 0.f;
-  float h = tf32_hi(x);
-  hi[e] = h;
-  lo[e] = x - h;
+  float x = (f < F && n < N) ? alpha[((long)s * F + f) * Npad_alpha + n] * ldexpf(1.f, fexp[s]) : 0.f;
+  split16(x, hi[e], lo[e]);
 }
 
 // ================================================================================================= kxt (SIMT)
 // One block = 128 candidates x all n in tiles of 128, 8x8 register micro-tiles (rows = candidates, cols = n):
-// Kxt[s][c][n] as float4 stores (256 B contiguous per 16 threads), mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.
-// grid = (Mc/128, S).  4 B written per (3D + 25) flops.
+// Kxt[s][c][n] * 2^ea as an fp16 (hi, lo) pair (two 8-byte stores per 4 values, 128 B contiguous per 16 threads),
+// ea = scale_exp(amp2[s] (1 + 1e-6));  mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.   grid = (Mc/128, S).
+// 4 B written per (3D + 25) flops.
 // Fast stationary kernels for the generator (float32): r = r2 * rsqrt(r2) and exp(x) = ex2.approx(x * log2 e), each ~2 ulp.
-// Their relative error (~2e-7) is below the tf32 hi/lo representation error of the operand (2^-21 = 4.8e-7) that
-// follows; the accurate sqrtf/expf versions cost ~25 of the ~110 instructions per element of this instruction-bound kernel.
+// Their relative error (~2e-7) is at the level of the float32 rounding already carried by r2;
+// the accurate sqrtf/expf versions cost ~25 of the ~110 instructions per element of this instruction-bound kernel.
 __device__ __forceinline__ float fast_exp(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
@@ -207,8 +290,8 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
                                                      const float* __restrict__ X, const float* __restrict__ Cc,
                                                      const float* __restrict__ inv_ls, const float* __restrict__ amp2,
                                                      const float* __restrict__ mean, const float* __restrict__ alpha,
-                                                     int Npad_alpha, float* __restrict__ kout,
-                                                     float* __restrict__ mu, int ldm) {
+                                                     int Npad_alpha, __half* __restrict__ khi,
+                                                     __half* __restrict__ klo, float* __restrict__ mu, int ldm) {
   constexpr int T = 128, LDT = T + kPad;
   __shared__ __align__(16) float stage[2][kKD][LDT];
   float (*cs)[LDT] = stage[0];                    // scaled candidates   [d][cand]
@@ -219,6 +302,7 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const float* ils = inv_ls + (long)s * D;
   const float a2 = amp2[s];
+  const float a2s = a2 * ldexpf(1.f, kx_exp(a2));     // amp2 * 2^ea: largest entry lands in [2^14, 2^15)
   const float* al = alpha + (long)s * Npad_alpha;
   float mdot[8];
 #pragma unroll
@@ -267,19 +351,20 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      float* ok = kout + ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
+      const long ok = ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        V4<float> kv4;
+        __half hh[4], ll[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = g * 4 + e;
           const int n = n0 + g * 64 + tx * 4 + e;
-          float kv = (n < N) ? a2 * kernel_of_r2_fast(kind, acc[r][c]) : 0.f;
-          mdot[r] = fmaf(av[c], kv, mdot[r]);
-          kv4.v[e] = kv;
+          const float kk = (n < N) ? kernel_of_r2_fast(kind, acc[r][c]) : 0.f;
+          mdot[r] = fmaf(av[c], kk, mdot[r]);
+          split16(a2s * kk, hh[e], ll[e]);
         }
-        st4(ok + g * 64 + tx * 4, kv4);      // plain float32: the tf32 hi/lo pair is formed inside the MMA kernel
+        *reinterpret_cast<uint2*>(khi + ok + g * 64 + tx * 4) = pack4(hh);
+        *reinterpret_cast<uint2*>(klo + ok + g * 64 + tx * 4) = pack4(ll);
       }
     }
   }
@@ -292,7 +377,7 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
     float v = 0.f;
     for (int q = 0; q < 16; ++q) v += red[q][tid];
     int gc = c_begin + c0 + tid;
-    if (gc < M) mu[(long)s * ldm + gc] = v + mean[s];
+    if (gc < M) mu[(long)s * ldm + gc] = fmaf(a2, v, mean[s]);
   }
 }
 
@@ -300,15 +385,19 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
 namespace tc {
 constexpr int BM = 128;        // candidates per tile (TMEM lanes, MMA M)
 constexpr int BN = 256;        // rows of Linv per group (MMA N, TMEM columns per accumulator)
-constexpr int BK = 16;         // k per stage: 16 x 4 B = one 64-byte swizzle row (BK = 32 -> 128-byte swizzle)
-constexpr int UK = 8;          // k per tcgen05.mma.kind::tf32
-constexpr int STAGES = 4;      // 4 x 48 KB: a TMA refill (~1.3 us from HBM) hides behind 3 stages of MMA (3 x 0.45 us)
+// Operand rows in shared memory are one 64-byte swizzle span: 16 tf32 (modes 2, 3: Cholesky update, triangular inverse)
+// or 32 fp16 (modes 0, 1: predict) -- identical tile bytes, descriptors and TMA box bytes for both element types; one
+// tcgen05.mma consumes 32 bytes of k (8 tf32 / 16 fp16), i.e. two MMAs per product per stage.
+constexpr int BK = 16;         // k per stage, tf32 elements
+constexpr int BK16 = 32;       // k per stage, fp16 elements
+constexpr int STAGES = 4;      // 4 x 48 KB: a TMA refill (~1.3 us from HBM) hides behind 3 stages of MMA
 constexpr int ROW_BYTES = BK * 4;                  // swizzle span = operand row in shared memory
-static_assert(ROW_BYTES == 64 || ROW_BYTES == 128, "operand rows must be one 64B or 128B swizzle span");
-constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int B_BYTES = BN * BK * 4;   // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
-constexpr int THREADS = 320;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue, warps 6-9: operand splitter
+static_assert(ROW_BYTES == 64 && BK16 * 2 == ROW_BYTES, "operand rows must be one 64B swizzle span in both element types");
+constexpr int UK_BYTES = 32;                       // k bytes per tcgen05.mma (kind::tf32: 8 x 4 B, kind::f16: 16 x 2 B)
+constexpr int A_BYTES = BM * ROW_BYTES;   // 8 KB
+constexpr int B_BYTES = BN * ROW_BYTES;   // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 48 KB
+constexpr int THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -348,7 +437,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 16;                                  // leading byte offset (ignored for swizzled K-major)
   d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;             // stride byte offset: 8 rows
   d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
-  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;         // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  d |= (uint64_t)4 << 61;                                  // SWIZZLE_64B
   return d;
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
@@ -360,6 +449,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 with fp16 A and B (format 0), fp32 accumulate
+constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdescF16), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -384,14 +483,16 @@ struct Args {
   float* dbg;                                     // optional [S][Mc][Np] dump of beta^T (tests only)
   // rectangular mode (fantasy means, OPT:609): B = alpha^T [S][ngroups*256][Np], full k range, one group per item,
   // the epilogue stores  D[c][f] + mean[s]  to mu_f[s][f][c_begin + c]  instead of reducing squares
-  int rect, F, M, c_begin, ldm;
+  int F, M, c_begin, ldm;
   const float* mean;
   float* mu_f;
+  // modes 0, 1: fp16 operands scaled by 2^ea (A: cross-covariance, ea = kx_exp(amp2[s])) and 2^bexp[s] (B: Linv or alpha^T)
+  int f16;
+  const float* amp2;
+  const int* bexp;
   // mode 2 (left-looking Cholesky update, potrf_tc): C[(jb+m)-th block row][block cols jb, jb+1] -= L[.., 0:jb] L[jb.., 0:jb]^T
   // mode 3 (triangular inverse, row block K): X[K, 0:K*128] = -Lt * X[0:K*128, 0:K*128], stored as X and X^T, hi/lo
   int mode;            // 0 tri (predict), 1 rect (fantasy means), 2 Cholesky update, 3 trtri row block
-  int a_raw;           // 1: the A operand arrives as plain float32 (map mAhi) and is split into tf32 hi/lo in shared
-                       //    memory by the splitter warps; 0: A arrives pre-split (maps mAhi, mAlo)
   int Npad, jb, ncols; // mode 2: factor leading dimension, first block column of the pair, valid columns (128 | 256)
   float* Cmat;         // mode 2: [S][Npad][Npad] matrix being factored
   int K;               // mode 3: row block
@@ -404,6 +505,7 @@ struct Item { int valid, rowA, rowB, k0, nk, s, tile, g, pr; };
 __device__ __forceinline__ Item get_item(const Args& p, long w, int h) {
   Item it;
   it.valid = 0; it.rowA = it.rowB = it.k0 = it.nk = it.s = it.tile = it.g = it.pr = 0;
+  const int bk = p.f16 ? BK16 : BK;
   if (p.mode <= 1) {
     it.pr = (int)(w % p.npairs);
     const long st = w / p.npairs;
@@ -411,7 +513,7 @@ __device__ __forceinline__ Item get_item(const Args& p, long w, int h) {
     it.s = (int)(st / p.ntiles);
     it.g = (h == 0) ? it.pr : p.ngroups - 1 - it.pr;
     if (h == 1 && (p.mode == 1 || it.g == it.pr)) return it;   // rect: one group per item; middle group of an odd count
-    it.nk = (p.mode == 1) ? p.Np / BK : (it.g + 1) * (BN / BK);
+    it.nk = (p.mode == 1) ? p.Np / bk : (it.g + 1) * (BN / bk);
     it.rowA = it.s * p.Mc + it.tile * BM;
     it.rowB = (it.s * p.ngroups + it.g) * BN;
     it.valid = 1;
@@ -421,7 +523,7 @@ __device__ __forceinline__ Item get_item(const Args& p, long w, int h) {
     it.s = (int)(w / p.ntiles);
     it.rowA = it.s * p.Npad + (p.jb + it.tile) * BM;
     it.rowB = it.s * p.Npad + p.jb * BM;            // block rows jb and jb+1 (256 rows)
-    it.nk = p.jb * BM / BK;
+    it.nk = p.jb * BM / bk;
     it.valid = 1;
   } else {
     if (h == 1) return it;
@@ -430,7 +532,7 @@ __device__ __forceinline__ Item get_item(const Args& p, long w, int h) {
     it.rowA = it.s * BM;                            // Lt: [S][128][ld]
     it.rowB = it.s * p.Np + it.tile * BN;           // X^T rows j
     it.k0 = it.tile * BN;
-    it.nk = (p.K * BM - it.tile * BN) / BK;
+    it.nk = (p.K * BM - it.tile * BN) / bk;
     it.valid = 1;
   }
   return it;
@@ -443,16 +545,15 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   // 1024-byte alignment required by the 128B swizzle atoms
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                 // [STAGES]  operands ready for the MMA (arrived by the 4 splitter warps)
+  uint64_t* full = bars;                 // [STAGES]  TMA bytes landed: operands ready for the MMA
   uint64_t* empty = bars + STAGES;       // [STAGES]  stage consumed (tcgen05.commit)
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
-  uint64_t* rawf = tempty + 2;           // [STAGES]  TMA bytes landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rawf + STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); mbar_init(&rawf[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -475,6 +576,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       const uint64_t hintB = 0x14F0000000000000ull;   // EVICT_LAST : the B operand is re-read by many items
       int stage = 0;
       uint32_t phase = 0;
+      const int bk = p.f16 ? BK16 : BK;
       for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
         for (int h = 0; h < 2; ++h) {
           const Item it = get_item(p, w, h);
@@ -482,12 +584,12 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           for (int kc = 0; kc < it.nk; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* sb = base + stage * STAGE_BYTES;
-            const int kk = it.k0 + kc * BK;
-            mbar_expect_tx(&rawf[stage], p.a_raw ? (A_BYTES + 2 * B_BYTES) : STAGE_BYTES);
-            tma_load_2d(&mAhi, &rawf[stage], sb, kk, it.rowA, hintA);
-            if (!p.a_raw) tma_load_2d(&mAlo, &rawf[stage], sb + A_BYTES, kk, it.rowA, hintA);
-            tma_load_2d(&mBhi, &rawf[stage], sb + 2 * A_BYTES, kk, it.rowB, hintB);
-            tma_load_2d(&mBlo, &rawf[stage], sb + 2 * A_BYTES + B_BYTES, kk, it.rowB, hintB);
+            const int kk = it.k0 + kc * bk;
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(&mAhi, &full[stage], sb, kk, it.rowA, hintA);
+            tma_load_2d(&mAlo, &full[stage], sb + A_BYTES, kk, it.rowA, hintA);
+            tma_load_2d(&mBhi, &full[stage], sb + 2 * A_BYTES, kk, it.rowB, hintB);
+            tma_load_2d(&mBlo, &full[stage], sb + 2 * A_BYTES + B_BYTES, kk, it.rowB, hintB);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -510,12 +612,22 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
             const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
             const uint64_t ahi = umma_desc(sa), alo = umma_desc(sa + A_BYTES);
             const uint64_t bhi = umma_desc(sa + 2 * A_BYTES), blo = umma_desc(sa + 2 * A_BYTES + B_BYTES);
+            if (p.f16) {
 #pragma unroll
-            for (int k = 0; k < BK / UK; ++k) {
-              const uint64_t ko = (uint64_t)((k * UK * 4) >> 4);     // advance inside the swizzle atom (16 B units)
-              umma_tf32(d, alo + ko, bhi + ko, (kc | k) ? 1u : 0u);  // small terms first
-              umma_tf32(d, ahi + ko, blo + ko, 1u);
-              umma_tf32(d, ahi + ko, bhi + ko, 1u);
+              for (int k = 0; k < ROW_BYTES / UK_BYTES; ++k) {
+                const uint64_t ko = (uint64_t)((k * UK_BYTES) >> 4);   // advance inside the swizzle atom (16 B units)
+                umma_f16(d, alo + ko, bhi + ko, (kc | k) ? 1u : 0u);   // small terms first
+                umma_f16(d, ahi + ko, blo + ko, 1u);
+                umma_f16(d, ahi + ko, bhi + ko, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < ROW_BYTES / UK_BYTES; ++k) {
+                const uint64_t ko = (uint64_t)((k * UK_BYTES) >> 4);
+                umma_tf32(d, alo + ko, bhi + ko, (kc | k) ? 1u : 0u);
+                umma_tf32(d, ahi + ko, blo + ko, 1u);
+                umma_tf32(d, ahi + ko, bhi + ko, 1u);
+              }
             }
             umma_commit(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -523,41 +635,6 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           umma_commit(&tfull[buf]);
           buf ^= 1;
           if (buf == 0) bphase ^= 1;
-        }
-      }
-    }
-  } else if (warp >= 6) {
-    // splitter warps: once the TMA bytes of a stage have landed, turn the float32 A tile into its tf32 (hi, lo) pair in
-    // place (hi = x & 0xffffe000 stays in the A slot, lo = x - hi goes to the A_lo slot), make the generic-proxy writes
-    // visible to the async proxy (tcgen05.mma reads shared memory through it) and release the stage to the MMA warp.
-    // The operation is elementwise on raw bytes, so it is oblivious to the swizzled layout.
-    const int ts = threadIdx.x - 192;       // 0..127
-    int stage = 0;
-    uint32_t phase = 0;
-    for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
-      for (int h = 0; h < 2; ++h) {
-        const Item it = get_item(p, w, h);
-        if (!it.valid) break;
-        for (int kc = 0; kc < it.nk; ++kc) {
-          mbar_wait(&rawf[stage], phase);
-          if (p.a_raw) {
-            float4* a = reinterpret_cast<float4*>(base + stage * STAGE_BYTES);
-            float4* l = reinterpret_cast<float4*>(base + stage * STAGE_BYTES + A_BYTES);
-#pragma unroll
-            for (int q = 0; q < A_BYTES / 16 / 128; ++q) {
-              float4 x = a[ts + q * 128], hh, ll;
-              hh.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); ll.x = x.x - hh.x;
-              hh.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); ll.y = x.y - hh.y;
-              hh.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); ll.z = x.z - hh.z;
-              hh.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); ll.w = x.w - hh.w;
-              a[ts + q * 128] = hh;
-              l[ts + q * 128] = ll;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -572,6 +649,8 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       for (int h = 0; h < 2; ++h) {
         const Item it = get_item(p, w, h);
         if (!it.valid) break;
+        // undo the exact power-of-two operand scaling of the fp16 path
+        const float scl = p.f16 ? ldexpf(1.f, -(kx_exp(p.amp2[it.s]) + p.bexp[it.s])) : 1.f;
         mbar_wait(&tfull[buf], bphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
@@ -583,13 +662,13 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           if (p.mode == 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]);
+              float v = __uint_as_float(r[j]) * scl;
               acc = fmaf(v, v, acc);
             }
             if (p.dbg) {
               float* o = p.dbg + ((long)it.s * p.Mc + it.tile * BM + row) * p.Np + it.g * BN + c0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]) * scl;
             }
           } else if (p.mode == 1) {
             const int gc = p.c_begin + it.tile * BM + row;
@@ -598,7 +677,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int f = it.g * BN + c0 + j;
-                if (f < p.F) p.mu_f[((long)it.s * p.F + f) * p.ldm + gc] = __uint_as_float(r[j]) + mu0;
+                if (f < p.F) p.mu_f[((long)it.s * p.F + f) * p.ldm + gc] = fmaf(__uint_as_float(r[j]), scl, mu0);
               }
             }
           } else if (p.mode == 2) {
@@ -685,9 +764,20 @@ static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t co
   cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+// same for an fp16 matrix: box = (BK16 cols) x (box_rows rows) -- the same 64-byte rows
+static int make_map_h(CUtensorMap* m, const __half* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return 1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)BK16, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
@@ -857,6 +947,28 @@ int trtri_split_tc(int Npad, int Np, int S, const float* L, const float* winv, f
   return check_launch("trtri_split_tc");
 }
 
+// fp16 operand copy of the explicit inverse for the predict GEMM: per-sample power-of-two scale + (hi, lo) split.
+// exps: [2*S] ints -- [0, S) receives the scale exponents, [S, 2S) is scratch (max |entry| bits).
+int linv_pack_f16(int Np, int S, const float* linv_hi, const float* linv_lo, __half* out_hi, __half* out_lo, int* exps,
+                  cudaStream_t st) {
+  if (Np <= 0 || Np % tc::BN) return -1;
+  if (S <= 0) return -2;
+  if (!linv_hi || !linv_lo || !out_hi || !out_lo || !exps) return -3;
+  unsigned* maxbits = reinterpret_cast<unsigned*>(exps + S);
+  cudaMemsetAsync(maxbits, 0, sizeof(unsigned) * S, st);
+  const long per4 = (long)Np * Np / 4;
+  const int gx = (int)std::min<long>((per4 + 255) / 256, 4L * num_sms());
+  timing_begin("linv_pack_f16", st);
+  linv_absmax_kernel<<<dim3(gx, S), 256, 0, st>>>(per4, reinterpret_cast<const float4*>(linv_hi),
+                                                  reinterpret_cast<const float4*>(linv_lo), maxbits);
+  linv_pack_f16_kernel<<<dim3(gx, S), 256, 0, st>>>(per4, reinterpret_cast<const float4*>(linv_hi),
+                                                    reinterpret_cast<const float4*>(linv_lo), maxbits,
+                                                    reinterpret_cast<uint2*>(out_hi), reinterpret_cast<uint2*>(out_lo), exps);
+  timing_end(st);
+  count_launch(2);
+  return check_launch("linv_pack_f16");
+}
+
 int linv_alpha(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y, const float* mean,
                float* alpha, int ld_alpha, float* tmp, cudaStream_t st) {
   if (N <= 0 || Np < N) return -1;
@@ -876,9 +988,9 @@ static bool tc_overlap_enabled() {
   if (v < 0) { const char* e = getenv("SMK_TC_OVERLAP"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
-// workspace: Kxt hi | Kxt lo | partial
+// workspace: Kxt hi (fp16) | Kxt lo (fp16) | partial | alpha^T hi | alpha^T lo | fantasy scale exponents
 static size_t tc_chunk_cands(int Np, int M, int S, size_t budget) {
-  size_t per_cand = (size_t)S * Np * sizeof(float);
+  size_t per_cand = (size_t)S * Np * 2 * sizeof(__half);
   size_t mpad = ((size_t)M + 127) / 128 * 128;
   size_t mc = budget / per_cand;
   if (mc >= mpad) return mpad;                  // everything in one chunk: single buffer
@@ -899,48 +1011,53 @@ static int fant_rows(int F) { return F > 1 ? ((F + tc::BN - 1) / tc::BN) * tc::B
 size_t predict_tc_workspace_bytes(int Np, int M, int S, int F) {
   size_t mc = tc_chunk_cands(Np, M, S, kTcBudget);
   int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2, nbuf = tc_nbuf(Np, M, S, kTcBudget);
-  return (size_t)nbuf * S * mc * Np * sizeof(float) + (size_t)npairs * S * mc * sizeof(float) +
-         2 * (size_t)S * fant_rows(F) * Np * sizeof(float) + 1024;
+  return (size_t)nbuf * S * mc * Np * 2 * sizeof(__half) + (size_t)npairs * S * mc * sizeof(float) +
+         2 * (size_t)S * fant_rows(F) * Np * sizeof(__half) + (size_t)S * sizeof(int) + 1024;
 }
 
 int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
-               const float* amp2, const float* mean, const float* linv_hi, const float* linv_lo, const float* alpha,
-               int Npad_alpha, float* mu, float* var, int ldm, void* workspace, size_t workspace_bytes, float* dbg,
-               int F, const float* alpha_f, float* mu_f, cudaStream_t st) {
+               const float* amp2, const float* mean, const __half* linv_hi, const __half* linv_lo, const int* linv_exp,
+               const float* alpha, int Npad_alpha, float* mu, float* var, int ldm, void* workspace,
+               size_t workspace_bytes, float* dbg, int F, const float* alpha_f, float* mu_f, cudaStream_t st) {
   if (kind < 0 || kind > 3) return -1;
   if (N <= 0) return -2;
   if (Np < N || Np % tc::BN) return -3;
   if (M <= 0) return -4;
   if (D <= 0) return -5;
   if (S <= 0) return -6;
-  if (!X || !Cc || !inv_ls || !amp2 || !mean || !linv_hi || !linv_lo || !alpha || !mu || !var) return -7;
-  if (ldm < M) return -18;
+  if (!X || !Cc || !inv_ls || !amp2 || !mean || !linv_hi || !linv_lo || !linv_exp || !alpha || !mu || !var) return -7;
+  if (ldm < M) return -19;
   const bool fant = (F > 1 && alpha_f && mu_f);
-  if (!workspace || workspace_bytes < predict_tc_workspace_bytes(Np, M, S, fant ? F : 1)) return -19;
+  if (!workspace || workspace_bytes < predict_tc_workspace_bytes(Np, M, S, fant ? F : 1)) return -20;
   const int Mc = (int)tc_chunk_cands(Np, M, S, kTcBudget);
   const int nbuf = tc_nbuf(Np, M, S, kTcBudget);
   const int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
-  float* khi = reinterpret_cast<float*>(workspace);                       // [nbuf][S][Mc][Np] float32 cross-covariance
-  float* partial = khi + (size_t)nbuf * S * Mc * Np;
+  const size_t kelems = (size_t)S * Mc * Np;                               // one Kxt buffer, elements per half-array
+  __half* kbase = reinterpret_cast<__half*>(workspace);                    // [nbuf]{hi [S][Mc][Np] | lo [S][Mc][Np]}
+  float* partial = reinterpret_cast<float*>(kbase + (size_t)nbuf * 2 * kelems);
   const int Fp = fant ? fant_rows(F) : 0;
-  float* ahi = partial + (size_t)npairs * S * Mc;               // alpha^T hi | lo  [S][Fp][Np]
-  float* alo = ahi + (size_t)S * Fp * Np;
+  __half* ahi = reinterpret_cast<__half*>(partial + (size_t)npairs * S * Mc);   // alpha^T hi | lo  [S][Fp][Np]
+  __half* alo = ahi + (size_t)S * Fp * Np;
+  int* fexp = reinterpret_cast<int*>(alo + (size_t)S * Fp * Np);
   CUtensorMap mFhi, mFlo;
   if (fant) {
     const long total = (long)S * Fp * Np;
-    alpha_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, Np, F, Fp, Npad_alpha, total, alpha_f, ahi, alo);
-    count_launch();
-    if (tc::make_map(&mFhi, ahi, (uint64_t)S * Fp, Np, tc::BN) || tc::make_map(&mFlo, alo, (uint64_t)S * Fp, Np, tc::BN))
+    alpha_absmax_kernel<<<S, 256, 0, st>>>(N, F, Npad_alpha, alpha_f, fexp);
+    alpha_pack_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, Np, F, Fp, Npad_alpha, total, alpha_f, fexp,
+                                                                           ahi, alo);
+    count_launch(2);
+    if (tc::make_map_h(&mFhi, ahi, (uint64_t)S * Fp, Np, tc::BN) || tc::make_map_h(&mFlo, alo, (uint64_t)S * Fp, Np, tc::BN))
       return 1999;
   }
 
   CUtensorMap mAhi[2], mAlo[2], mBhi, mBlo;
   for (int b = 0; b < nbuf; ++b) {
-    float* kh = khi + (size_t)b * S * Mc * Np;
-    if (tc::make_map(&mAhi[b], kh, (uint64_t)S * Mc, Np, tc::BM)) return 1999;   // cuTensorMapEncodeTiled failed
-    mAlo[b] = mAhi[b];                                                           // unused in a_raw mode
+    __half* kh = kbase + (size_t)b * 2 * kelems;
+    if (tc::make_map_h(&mAhi[b], kh, (uint64_t)S * Mc, Np, tc::BM) ||
+        tc::make_map_h(&mAlo[b], kh + kelems, (uint64_t)S * Mc, Np, tc::BM))
+      return 1999;                                                              // cuTensorMapEncodeTiled failed
   }
-  if (tc::make_map(&mBhi, linv_hi, (uint64_t)S * Np, Np, tc::BN) || tc::make_map(&mBlo, linv_lo, (uint64_t)S * Np, Np, tc::BN))
+  if (tc::make_map_h(&mBhi, linv_hi, (uint64_t)S * Np, Np, tc::BN) || tc::make_map_h(&mBlo, linv_lo, (uint64_t)S * Np, Np, tc::BN))
     return 1999;
   static bool attr = false;
   if (!attr) {
@@ -968,23 +1085,23 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   int ci = 0;
   for (int c_begin = 0; c_begin < M; c_begin += Mc, ++ci) {
     const int b = overlap ? (ci & 1) : 0;
-    float* kh = khi + (size_t)b * S * Mc * Np;
+    __half* kh = kbase + (size_t)b * 2 * kelems;
     const int mc_used = min(Mc, ((M - c_begin) + 127) / 128 * 128);
     if (overlap && ci >= 2) cudaStreamWaitEvent(aux, ev_mma[b], 0);      // buffer b is free again
     timing_begin("kxt_kernel", kst);
     kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, kst>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
-                                                        alpha, Npad_alpha, kh, mu, ldm);
+                                                        alpha, Npad_alpha, kh, kh + kelems, mu, ldm);
     timing_end(kst);
     if (overlap) {
       cudaEventRecord(ev_kxt[b], aux);
       cudaStreamWaitEvent(st, ev_kxt[b], 0);
     }
     tc::Args a;
+    tc_args_init(a);
     a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
     a.partial = partial; a.dbg = dbg;
-    a.rect = 0; a.F = 0; a.M = M; a.c_begin = c_begin; a.ldm = ldm; a.mean = mean; a.mu_f = nullptr;
-    a.mode = 0; a.a_raw = 1; a.Npad = 0; a.jb = 0; a.ncols = 0; a.Cmat = nullptr; a.K = 0;
-    a.xhi = a.xlo = a.xthi = a.xtlo = nullptr;
+    a.M = M; a.c_begin = c_begin; a.ldm = ldm; a.mean = mean;
+    a.mode = 0; a.f16 = 1; a.amp2 = amp2; a.bexp = linv_exp;
     long nitems = (long)S * a.ntiles * npairs;
     int grid = (int)std::min<long>(nitems, num_sms());
     timing_begin("predict_tc_kernel", st);
@@ -995,7 +1112,7 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     count_launch(3);
     if (fant) {      // fantasy means: same Kxt chunk against alpha^T, rectangular k range (OPT:609)
       tc::Args r = a;
-      r.rect = 1; r.mode = 1; r.F = F; r.mu_f = mu_f; r.ngroups = Fp / tc::BN; r.npairs = r.ngroups;
+      r.mode = 1; r.F = F; r.mu_f = mu_f; r.bexp = fexp; r.ngroups = Fp / tc::BN; r.npairs = r.ngroups;
       long nit = (long)S * r.ntiles * r.npairs;
       int gr = (int)std::min<long>(nit, num_sms());
       timing_begin("predict_tc_kernel_rect", st);

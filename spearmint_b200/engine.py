@@ -81,7 +81,7 @@ class Factor(object):
                   "potrf")
 
     def linv(self):
-        """(hi, lo, Np): explicit inverse of the factor split for the 3xTF32 tensor-core predict; computed once."""
+        """(hi, lo, Np): explicit inverse of the factor as a tf32 hi/lo pair of float32 arrays; computed once."""
         if getattr(self, "_linv", None) is None:
             eng, L = self.eng, _lib.lib()
             S = self.hb.S
@@ -100,6 +100,21 @@ class Factor(object):
                                             nb, eng.stream()), "trtri_split")
             self._linv = (hi, lo, Np)
         return self._linv
+
+    def linv16(self):
+        """(h16, l16, exps, Np): the GEMM operand copy of the inverse -- per-sample power-of-two scale 2^exps[s] and the
+        fp16 (hi, lo) pair consumed by the 3xFP16 tensor-core predict; computed once."""
+        if getattr(self, "_linv16", None) is None:
+            eng, L = self.eng, _lib.lib()
+            hi, lo, Np = self.linv()
+            S = self.hb.S
+            h16 = torch.empty((S, Np, Np), dtype=torch.float16, device=eng.device)
+            l16 = torch.empty((S, Np, Np), dtype=torch.float16, device=eng.device)
+            exps = torch.empty((2 * S,), dtype=torch.int32, device=eng.device)
+            check(L.smk_linv_pack_f16(Np, S, ptr(hi), ptr(lo), ptr(h16), ptr(l16), ptr(exps), eng.stream()),
+                  "linv_pack_f16")
+            self._linv16 = (h16, l16, exps, Np)
+        return self._linv16
 
     def alpha_via_linv(self, y):
         """alpha = Linv^T Linv (y - mean), [S][1][Npad]; needs the explicit inverse (tensor-core predict path)."""
@@ -165,7 +180,7 @@ class GPEIEngine(object):
         self.NB = _lib.lib().smk_block(self.esize)
         self._ws = None
         self._ws_tc = None
-        # fused-predict implementation: "tc" = tcgen05/TMEM/TMA 3xTF32 kernel (float32 only), "simt" = register-tiled FMA
+        # fused-predict implementation: "tc" = tcgen05/TMEM/TMA 3xFP16 kernel (float32 in/out), "simt" = register-tiled FMA
         self.predict_impl = os.environ.get("SMK_PREDICT_IMPL", "tc" if dtype == torch.float32 else "simt")
         if dtype != torch.float32:
             self.predict_impl = "simt"
@@ -246,15 +261,15 @@ class GPEIEngine(object):
         var = torch.empty((hb.S, ldm), dtype=dt, device=self.device)
         if (impl or self.predict_impl) == "tc" and isinstance(fac, Factor):
             L = _lib.lib()
-            hi, lo, Np = fac.linv()
+            h16, l16, lexp, Np = fac.linv16()
             nb = L.smk_predict_tc_workspace_bytes(Np, M, hb.S, F if alpha_f is not None else 1)
             if self._ws_tc is None or self._ws_tc.numel() < nb:
                 self._ws_tc = None
                 self._ws_tc = torch.empty((nb,), dtype=torch.uint8, device=self.device)
             mu_f = torch.empty((hb.S, F, ldm), dtype=dt, device=self.device) if alpha_f is not None else None
             check(L.smk_predict_tc_f32(KINDS[kind], fac.N, Np, M, fac.D, hb.S, ptr(fac.X), ptr(C_dev), ptr(hb.inv_ls),
-                                       ptr(hb.amp2), ptr(hb.mean), ptr(hi), ptr(lo), ptr(alpha), fac.Npad, ptr(mu),
-                                       ptr(var), ldm, ptr(self._ws_tc), nb, ptr(dbg_beta),
+                                       ptr(hb.amp2), ptr(hb.mean), ptr(h16), ptr(l16), ptr(lexp), ptr(alpha), fac.Npad,
+                                       ptr(mu), ptr(var), ldm, ptr(self._ws_tc), nb, ptr(dbg_beta),
                                        F if alpha_f is not None else 1, ptr(alpha_f), ptr(mu_f), self.stream()),
                   "predict_tc")
             if alpha_f is not None:

@@ -198,8 +198,8 @@ def test_topk_matches_numpy(engines, M, k):
 # ------------------------------------------------------------------------------------------------ tensor-core predict
 @pytest.mark.parametrize("D,N,M", [(6, 100, 128), (8, 300, 1000), (3, 520, 257), (40, 260, 200)])
 def test_predict_tc_beta_and_moments(engines, D, N, M):
-    """tcgen05 3xTF32 path: the dumped beta^T = Kx^T L^-T tile product (descriptor / swizzle / pipeline check) and
-    the resulting moments, against the oracle."""
+    """tcgen05 3xFP16 path: the fp16 operand pack of L^-1 (scale + hi/lo), the dumped beta^T = Kx^T L^-T tile product
+    (descriptor / swizzle / pipeline / un-scaling check) and the resulting moments, against the oracle."""
     import torch
     from spearmint_b200 import _lib
     eng = engines["f32"]
@@ -214,6 +214,15 @@ def test_predict_tc_beta_and_moments(engines, D, N, M):
     mu, var, ldm = eng.predict("Matern52", fac, eng.to_dev(Cd), alpha.view(hb.S, fac.Npad), impl="tc", dbg_beta=dbg)
     mu2, var2, _ = eng.predict("Matern52", fac, eng.to_dev(Cd), alpha.view(hb.S, fac.Npad), impl="simt")
     linv = (hi.double() + lo.double()).cpu().numpy()
+    h16, l16, exps, _ = fac.linv16()
+    exps = exps.cpu().numpy()[:hb.S]
+    for s in range(hb.S):       # exact power-of-two scale into [2^14, 2^15), hi + lo reproduces the float32 inverse to 2^-21
+        sc = np.abs(linv[s]).max() * 2.0 ** exps[s]
+        assert 2.0 ** 14 <= sc < 2.0 ** 15, (sc, exps[s])
+        rec = (h16[s].double() + l16[s].double()).cpu().numpy() * 2.0 ** -float(exps[s])
+        assert np.abs(rec - linv[s]).max() <= 2.0 ** -21 * np.abs(linv[s]).max()
+        big = np.abs(linv[s]) >= 2.0 ** -17 * np.abs(linv[s]).max()
+        assert np.all(np.abs(rec - linv[s])[big] <= 2.0 ** -21 * np.abs(linv[s])[big])
     dbg, mu, var = dbg.double().cpu().numpy(), mu.double().cpu().numpy(), var.double().cpu().numpy()
     for s, h in enumerate(hs):
         m_ref, v_ref, L, _ = O.predict("Matern52", h, X, Cd, y)
@@ -231,3 +240,25 @@ def test_predict_tc_beta_and_moments(engines, D, N, M):
     # and against the SIMT kernel of the same library
     np.testing.assert_allclose(var[:, :M], var2.double().cpu().numpy()[:, :M], rtol=1e-3, atol=floor)
     np.testing.assert_allclose(mu[:, :M], mu2.double().cpu().numpy()[:, :M], rtol=1e-4, atol=floor)
+
+
+@pytest.mark.parametrize("amp2,noise", [(3e-5, 1e-8), (2.5e3, 1.0), (1.0, 1e-6), (7e-3, 5e-2)])
+def test_predict_tc_operand_scaling_range(engines, amp2, noise):
+    """The fp16 operand scaling follows amp2 (cross-covariance) and max|L^-1| (which follows 1/sqrt(noise + 1e-6 amp2)):
+    moments stay at float32 accuracy over a wide range of both."""
+    eng = engines["f32"]
+    D, N, M = 5, 300, 384
+    X, Cd, y, _ = _problem(D, N, M, 1, 5)
+    rs = np.random.RandomState(9)
+    hs = [(0.0, noise, amp2, rs.uniform(0.3, 2.0, D)), (0.2, noise * 3, amp2 * 0.37, rs.uniform(0.3, 2.0, D))]
+    y = y * np.sqrt(amp2)
+    hb = eng.hypers(hs, "Matern52")
+    fac = eng.factor("Matern52", eng.to_dev(X), hb)
+    fac.check_pd()
+    alpha, _, _ = fac.solve(eng.to_dev(y), F=1)
+    mu, var, _ = eng.predict("Matern52", fac, eng.to_dev(Cd), alpha.view(hb.S, fac.Npad), impl="tc")
+    mu, var = mu.double().cpu().numpy(), var.double().cpu().numpy()
+    for s, h in enumerate(hs):
+        m_ref, v_ref, _, _ = O.predict("Matern52", h, X, Cd, y)
+        np.testing.assert_allclose(var[s, :M], v_ref, rtol=1e-3, atol=3e-4 * h[2])
+        np.testing.assert_allclose(mu[s, :M], m_ref, rtol=1e-4, atol=1e-3 * np.sqrt(amp2))
