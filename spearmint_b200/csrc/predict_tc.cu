@@ -268,23 +268,37 @@ __global__ void alpha_pack_f16_kernel(int N, int Np, int F, int Fp, int Npad_alp
 // Kxt[s][c][n] * 2^ea as an fp16 (hi, lo) pair (two 8-byte stores per 4 values, 128 B contiguous per 16 threads),
 // ea = scale_exp(amp2[s] (1 + 1e-6));  mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.   grid = (Mc/128, S).
 // 4 B written per (3D + 25) flops.
-// Fast stationary kernels for the generator (float32): r = r2 * rsqrt(r2) and exp(x) = ex2.approx(x * log2 e), each ~2 ulp.
-// Their relative error (~2e-7) is at the level of the float32 rounding already carried by r2;
-// the accurate sqrtf/expf versions cost ~25 of the ~110 instructions per element of this instruction-bound kernel.
-__device__ __forceinline__ float fast_exp(float x) {
+// Fast stationary kernels for the generator (float32): sqrt.approx / ex2.approx (MUFU, ~1-2 ulp) instead of the accurate
+// sqrtf/expf sequences -- their relative error (~2e-7) is at the level of the float32 rounding already carried by r2.
+// The kernel is issue-bound (ncu r01: 110 instructions per element, 73% issue-slot utilisation, FMA pipe 53%), so the
+// arithmetic is written with Blackwell's packed float32 instructions (FADD2 / FFMA2 / FMUL2: two lanes per issue slot).
+__device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float kernel_of_r2_fast(int kind, float r2) {
-  if (kind <= 1) return fast_exp(-0.5f * r2);
-  float r = (r2 > 0.f) ? r2 * rsqrtf(r2) : 0.f;
-  if (kind == 2) { float a = 1.7320508075688772f * r; return (1.f + a) * fast_exp(-a); }
-  float a = 2.23606797749979f * r;
-  return (1.f + a + (5.0f / 3.0f) * r2) * fast_exp(-a);
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 kernel_pair_fast(int kind, float2 r2) {
+  constexpr float kL2E = 1.4426950408889634f;
+  if (kind <= 1) {                                            // SE / ARDSE: exp(-r2 / 2)
+    const float2 t = __fmul2_rn(r2, dup2(-0.5f * kL2E));
+    return make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  }
+  const float2 r = make_float2(sqrt_approx(r2.x), sqrt_approx(r2.y));
+  const float c = (kind == 2) ? 1.7320508075688772f : 2.23606797749979f;
+  const float2 t = __fmul2_rn(r, dup2(-c * kL2E));
+  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  float2 p = __ffma2_rn(r, dup2(c), dup2(1.f));               // Matern32: (1 + sqrt3 r) e^-sqrt3 r
+  if (kind == 3) p = __ffma2_rn(r2, dup2(5.0f / 3.0f), p);    // Matern52: (1 + sqrt5 r + 5/3 r2) e^-sqrt5 r
+  return __fmul2_rn(p, e);
 }
 
-constexpr int kKD = 16;   // D chunk staged in shared memory (17 KB total: co-resides with the 198 KB MMA block)
+constexpr int kKD = 16;   // D chunk staged in shared memory (25 KB total)
 
 __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, int M, int c_begin, int Mc, int D,
                                                      const float* __restrict__ X, const float* __restrict__ Cc,
@@ -292,86 +306,103 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
                                                      const float* __restrict__ mean, const float* __restrict__ alpha,
                                                      int Npad_alpha, __half* __restrict__ khi,
                                                      __half* __restrict__ klo, float* __restrict__ mu, int ldm) {
-  constexpr int T = 128, LDT = T + kPad;
-  __shared__ __align__(16) float stage[2][kKD][LDT];
-  float (*cs)[LDT] = stage[0];                    // scaled candidates   [d][cand]
-  float (*xs)[LDT] = stage[1];                    // scaled observations [d][n]
-  float (*red)[T] = reinterpret_cast<float (*)[T]>(&stage[0][0][0]);   // [16][T] epilogue scratch (aliases the staging)
-  static_assert(16 * T <= 2 * kKD * LDT, "reduction scratch must fit in the staging buffers");
+  constexpr int T = 128, LDC = T + 2, LDX = T + kPad;
+  __shared__ __align__(16) float2 cs[kKD][LDC];   // scaled candidates, each value duplicated (v, v): packed-op operand
+  __shared__ __align__(16) float xs[kKD][LDX];    // MINUS the scaled observations [d][n]
+  float (*red)[T] = reinterpret_cast<float (*)[T]>(&cs[0][0]);   // [16][T] epilogue scratch (aliases the staging)
+  static_assert(16 * T * sizeof(float) <= sizeof(float2) * kKD * LDC, "reduction scratch must fit in the staging buffer");
+  static_assert((LDC * sizeof(float2)) % 16 == 0 && (LDX * sizeof(float)) % 16 == 0, "128-bit shared loads");
   const int s = blockIdx.y, c0 = blockIdx.x * T;  // c0 relative to the chunk
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const float* ils = inv_ls + (long)s * D;
   const float a2 = amp2[s];
-  const float a2s = a2 * ldexpf(1.f, kx_exp(a2));     // amp2 * 2^ea: largest entry lands in [2^14, 2^15)
+  const float2 a2s = dup2(a2 * ldexpf(1.f, kx_exp(a2)));     // amp2 * 2^ea: largest entry lands in [2^14, 2^15)
   const float* al = alpha + (long)s * Npad_alpha;
-  float mdot[8];
+  float2 mdot[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) mdot[r] = 0.f;
+  for (int r = 0; r < 8; ++r) mdot[r] = make_float2(0.f, 0.f);
 
   for (int n0 = 0; n0 < Np; n0 += T) {
-    float acc[8][8];
+    float2 acc[8][4];          // rows: 8 candidates (tile_row), columns: 4 pairs of n (pair cp = n-offsets 2cp, 2cp+1)
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+      for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
     for (int d0 = 0; d0 < D; d0 += kKD) {
       __syncthreads();
       for (int e = tid; e < T * kKD; e += 256) {
         int row = e / kKD, dd = e % kKD, d = d0 + dd;
         int gc = min(c_begin + c0 + row, M - 1), n = n0 + row;
         float sc = (d < D) ? ils[d] : 0.f;
-        cs[dd][row] = (d < D) ? Cc[(long)gc * D + d] * sc : 0.f;
-        xs[dd][row] = (d < D && n < N) ? X[(long)n * D + d] * sc : 0.f;
+        cs[dd][row] = dup2((d < D) ? Cc[(long)gc * D + d] * sc : 0.f);
+        xs[dd][row] = (d < D && n < N) ? -X[(long)n * D + d] * sc : 0.f;
       }
       __syncthreads();
       const int dmax = min(kKD, D - d0);
       for (int dd = 0; dd < dmax; ++dd) {
-        float a[8], b[8];
+        float2 b[4];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          V4<float> t = ld4(&cs[dd][g * 64 + ty * 4]);
-          V4<float> u = ld4(&xs[dd][g * 64 + tx * 4]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { a[g * 4 + e] = t.v[e]; b[g * 4 + e] = u.v[e]; }
+          const V4<float> u = ld4(&xs[dd][g * 64 + tx * 4]);
+          b[2 * g] = make_float2(u.v[0], u.v[1]);
+          b[2 * g + 1] = make_float2(u.v[2], u.v[3]);
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int g = 0; g < 2; ++g) {
+          const float4 p0 = *reinterpret_cast<const float4*>(&cs[dd][g * 64 + ty * 4]);
+          const float4 p1 = *reinterpret_cast<const float4*>(&cs[dd][g * 64 + ty * 4 + 2]);
+          const float2 a[4] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y),
+                               make_float2(p1.z, p1.w)};
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float df = a[r] - b[c];
-            acc[r][c] = fmaf(df, df, acc[r][c]);
-          }
+          for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float2 df = __fadd2_rn(a[rr], b[c]);
+              acc[g * 4 + rr][c] = __ffma2_rn(df, df, acc[g * 4 + rr][c]);
+            }
+        }
       }
     }
-    float av[8];
+    const bool edge = (n0 + T > N);
+    float2 av[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      int n = n0 + tile_col(tx, c);
-      av[c] = (n < N) ? al[n] : 0.f;
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + (c >> 1) * 64 + tx * 4 + (c & 1) * 2;
+      av[c] = make_float2((n < N) ? al[n] : 0.f, (n + 1 < N) ? al[n + 1] : 0.f);
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const long ok = ((long)s * Mc + c0 + tile_row(ty, r)) * Np + n0;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        __half hh[4], ll[4];
+        __half2 hh[2], ll[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = g * 4 + e;
-          const int n = n0 + g * 64 + tx * 4 + e;
-          const float kk = (n < N) ? kernel_of_r2_fast(kind, acc[r][c]) : 0.f;
-          mdot[r] = fmaf(av[c], kk, mdot[r]);
-          split16(a2s * kk, hh[e], ll[e]);
+        for (int q = 0; q < 2; ++q) {
+          const int c = 2 * g + q;
+          float2 kk = kernel_pair_fast(kind, acc[r][c]);
+          if (edge) {                                   // padded observations carry no covariance (Linv pad rows are identity)
+            const int n = n0 + g * 64 + tx * 4 + q * 2;
+            if (n >= N) kk.x = 0.f;
+            if (n + 1 >= N) kk.y = 0.f;
+          }
+          mdot[r] = __ffma2_rn(av[c], kk, mdot[r]);
+          const float2 v = __fmul2_rn(kk, a2s);
+          hh[q] = __floats2half2_rn(v.x, v.y);
+          const float2 hf = __half22float2(hh[q]);
+          ll[q] = __floats2half2_rn(v.x - hf.x, v.y - hf.y);
         }
-        *reinterpret_cast<uint2*>(khi + ok + g * 64 + tx * 4) = pack4(hh);
-        *reinterpret_cast<uint2*>(klo + ok + g * 64 + tx * 4) = pack4(ll);
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<unsigned*>(&hh[0]); ph.y = *reinterpret_cast<unsigned*>(&hh[1]);
+        pl.x = *reinterpret_cast<unsigned*>(&ll[0]); pl.y = *reinterpret_cast<unsigned*>(&ll[1]);
+        *reinterpret_cast<uint2*>(khi + ok + g * 64 + tx * 4) = ph;
+        *reinterpret_cast<uint2*>(klo + ok + g * 64 + tx * 4) = pl;
       }
     }
   }
   // mean: reduce the per-thread row partials over the 16 column-threads (fixed order -> deterministic)
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 8; ++r) red[tx][tile_row(ty, r)] = mdot[r];
+  for (int r = 0; r < 8; ++r) red[tx][tile_row(ty, r)] = mdot[r].x + mdot[r].y;
   __syncthreads();
   if (tid < T) {
     float v = 0.f;
