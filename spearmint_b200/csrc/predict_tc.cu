@@ -519,6 +519,7 @@ struct Args {
   float* mu_f;
   // modes 0, 1: fp16 operands scaled by 2^ea (A: cross-covariance, ea = kx_exp(amp2[s])) and 2^bexp[s] (B: Linv or alpha^T)
   int f16;
+  int a_evict_first;   // experiment switch (SMK_TC_A_EVICT_FIRST=1): stream the mode-0 A operand with EVICT_FIRST
   const float* amp2;
   const int* bexp;
   // mode 2 (left-looking Cholesky update, potrf_tc): C[(jb+m)-th block row][block cols jb, jb+1] -= L[.., 0:jb] L[jb.., 0:jb]^T
@@ -603,7 +604,10 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   // concurrently on neighbouring SMs and hit L2 for the Kxt slab.
   if (warp == 0) {
     if (lane == 0) {
-      const uint64_t hintA = 0x12F0000000000000ull;   // EVICT_FIRST: the A operand is streamed
+      // A (cross-covariance slab of one candidate tile, 2 MB) is read by the 8 row-group-pair CTAs of that tile at
+      // different times: EVICT_FIRST made 7 of the 8 reads come from HBM (ncu r01: 103 GB read per launch vs 24 GB
+      // algorithmic); mode 0 therefore keeps it under the normal policy.  Modes 2/3 stream A once.
+      const uint64_t hintA = (p.mode == 0 && !p.a_evict_first) ? 0x1000000000000000ull : 0x12F0000000000000ull;   // EVICT_NORMAL : EVICT_FIRST
       const uint64_t hintB = 0x14F0000000000000ull;   // EVICT_LAST : the B operand is re-read by many items
       int stage = 0;
       uint32_t phase = 0;
@@ -1133,6 +1137,7 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     a.partial = partial; a.dbg = dbg;
     a.M = M; a.c_begin = c_begin; a.ldm = ldm; a.mean = mean;
     a.mode = 0; a.f16 = 1; a.amp2 = amp2; a.bexp = linv_exp;
+    { const char* e = getenv("SMK_TC_A_EVICT_FIRST"); a.a_evict_first = (e && e[0] == '1') ? 1 : 0; }
     long nitems = (long)S * a.ntiles * npairs;
     int grid = (int)std::min<long>(nitems, num_sms());
     timing_begin("predict_tc_kernel", st);
