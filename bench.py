@@ -4,14 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
 A "step" is one pass of ``ei_over_hypers`` (chooser/GPEIOptChooser.py:331-341 of the reference) over the
-whole candidate grid for all S hyper-samples: K build -> Cholesky -> alpha -> fused predict -> EI sweep
-(-> all-reduce of the per-candidate EI sum when N > 1) -> argmax.
+whole candidate grid for all S hyper-samples: K build -> Cholesky -> explicit inverse + alpha -> cross-covariance
+generator -> tcgen05 predict GEMM (3xFP16 scaled split) -> EI sweep (-> all-reduce of the per-candidate EI sum when
+N > 1) -> argmax.
 
   value : M / step-time with X, candidates, values and hyper-samples already resident in HBM.
   e2e   : the same metric through the host-facing call (numpy in, (M,S) EI matrix out), host<->device copies
           inside the timed region.
-  roofline     : the dominant kernel (predict_kernel, the N^2*M triangular solve), algorithmic flops / its
-                 CUDA-event time vs the measured dense bf16 tensor peak (MEASURED_PEAKS.json).
+  roofline     : the dominant kernel (tc::predict_tc_kernel, the N^2*M triangular-solve term as a GEMM against the
+                 explicit inverse), algorithmic flops / its CUDA-event time vs the measured dense bf16 tensor peak
+                 (MEASURED_PEAKS.json); traffic = DRAM bytes per launch from the ncu capture in profiles/.
   cpu_baseline : the oracle port (numpy/scipy, the reference's own operation sequence) timed on this box's
                  host cores on a bounded sample of the same workload and extrapolated linearly (the reference
                  loop is exactly linear in S and in M for fixed N).
@@ -61,6 +63,20 @@ def synth(D, N, M, S):
 def flops_per_pair(N, D):
     """algorithmic flops per (candidate, hyper-sample) pair."""
     return float(N) * N + 2.0 * N * D + 4.0 * N + 25.0 * N + 40.0
+
+
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE predict-GEMM launch over a full 32768-candidate chunk
+# of the headline workload on one GPU, from the `ncu --set full` capture summarised in profiles/ (bench.py never runs
+# under a profiler).  A step has 3 such launches + a 1696-candidate tail; the per-launch average is reported.
+NCU_TRAFFIC = {"headline": {"bytes_per_full_chunk_launch": 37.82e9, "chunk_cands": 32768,
+                            "source": "profiles/r01_predict_tc_final_ncu.md"}}
+
+
+def ncu_traffic(workload, impl, world, M, launches_per_step):
+    t = NCU_TRAFFIC.get(workload)
+    if t is None or impl != "tc" or world != 1:
+        return None
+    return t["bytes_per_full_chunk_launch"] * (float(M) / t["chunk_cands"]) / max(1, launches_per_step)
 
 
 def peaks():
@@ -305,7 +321,8 @@ def run_b200_arm(args, D, N, M, S):
         roof = {"kernel": "smk::tc::predict_tc_kernel (tcgen05.mma kind::f16, 3xFP16 scaled split, fp32 accumulate)" if impl == "tc"
                 else "smk::predict_kernel<float> (SIMT FMA)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": (achieved / pk["tensor_sustained"]) if achieved else None, "traffic": None,
+                "frac": (achieved / pk["tensor_sustained"]) if achieved else None,
+                "traffic": ncu_traffic(args.workload, impl, world, M, n_launch_step),
                 "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": alg / n_launch_step, "launches_per_step": n_launch_step,
                 "kernel_ms_per_launch": kms_step / n_launch_step, "kernel_ms_per_step": kms_step,
