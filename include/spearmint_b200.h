@@ -140,6 +140,14 @@ int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* 
 size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F);
 /* F > 1 with alpha_f [S][F][Npad_alpha] and mu_f [S][F][ldm] non-NULL: additionally the fantasy means
  * mu_f[s][f][j] = cov(X, C_j)' alpha_f[s][f] + mean[s]  (OPT:609) as a second tcgen05 GEMM on the same Kxt chunk. */
+/* The cross-covariance operand generator on its own (cov(comp, cand), OPT:536, and the mean OPT:544), one chunk:
+ * k_h16 / k_l16: [S][ceil128(M)][Np] halves = amp2 k(X_n, C_c) * 2^ea as an fp16 (hi, lo) pair, ea = 15 - ceil(log2(
+ * amp2 (1 + 1e-6) 1.00001));  mu: [S][ldm].  impl 0: packed-float32 SIMT kernel (any D, S); impl 1: tensor-core kernel
+ * (q = (x - c)^2 once per pair, contraction over dimensions for all samples on tcgen05; D <= 32, S <= 64, else -1).  */
+size_t smk_kxt_pack_workspace_bytes(int Np, int M, int S);
+int smk_kxt_pack_f16(int impl, int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
+                     const float* inv_ls, const float* amp2, const float* mean, const float* alpha, int Npad_alpha,
+                     void* k_h16, void* k_l16, float* mu, int ldm, void* workspace, size_t workspace_bytes, void* stream);
 int smk_linv_pack_f16(int Np, int S, const float* linv_hi, const float* linv_lo, void* linv_h16, void* linv_l16,
                       int* linv_exp, void* stream);
 int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,

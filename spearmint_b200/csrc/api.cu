@@ -77,6 +77,9 @@ size_t trtri_tc_workspace_bytes(int, int, int);
 int trtri_split_tc(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
 int linv_alpha(int, int, int, const float*, const float*, const float*, const float*, float*, int, float*, cudaStream_t);
 int linv_pack_f16(int, int, const float*, const float*, __half*, __half*, int*, cudaStream_t);
+size_t kxt_pack_workspace_bytes(int, int, int);
+int kxt_pack(int, int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
+             const float*, int, __half*, __half*, float*, int, void*, size_t, cudaStream_t);
 int predict_tc(int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
                const __half*, const __half*, const int*, const float*, int, float*, float*, int, void*, size_t, float*,
                int, const float*, float*, cudaStream_t);
@@ -193,6 +196,14 @@ int smk_trtri_split_tc_f32(int Npad, int Np, int S, const float* L, const float*
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream) {
   return linv_alpha(N, Np, S, linv_hi, linv_lo, y, mean, alpha, ld_alpha, tmp, ST(stream));
+}
+size_t smk_kxt_pack_workspace_bytes(int Np, int M, int S) { return kxt_pack_workspace_bytes(Np, M, S); }
+int smk_kxt_pack_f16(int impl, int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
+                     const float* inv_ls, const float* amp2, const float* mean, const float* alpha, int Npad_alpha,
+                     void* k_h16, void* k_l16, float* mu, int ldm, void* workspace, size_t workspace_bytes, void* stream) {
+  return kxt_pack(impl, kind, N, Np, M, D, S, X, C, inv_ls, amp2, mean, alpha, Npad_alpha,
+                  reinterpret_cast<__half*>(k_h16), reinterpret_cast<__half*>(k_l16), mu, ldm, workspace, workspace_bytes,
+                  ST(stream));
 }
 int smk_linv_pack_f16(int Np, int S, const float* linv_hi, const float* linv_lo, void* linv_h16, void* linv_l16,
                       int* linv_exp, void* stream) {

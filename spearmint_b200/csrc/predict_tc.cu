@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace smk {
 
@@ -168,32 +169,6 @@ __global__ void __launch_bounds__(256) linv_mtv_kernel(int N, int Np, int ld_alp
   if (ph == 0 && c < ld_alpha) alpha[(long)s * ld_alpha + c] = (c < N) ? red[0][cl] + red[1][cl] + red[2][cl] + red[3][cl] : 0.f;
 }
 
-// ---------------------------------------------------------------------------------------------- fp16 operand packing
-// The predict GEMMs run as 3 x FP16 tensor products (hi*hi + hi*lo + lo*hi, fp32 accumulate).  fp16 carries the same
-// 11-bit significand as tf32 at twice the tensor rate but only 5 exponent bits, so every operand matrix is multiplied
-// by an exact power of two that puts its largest |entry| in [2^14, 2^15) before the round-to-nearest split
-//     hi = fp16(x * 2^e),   lo = fp16(x * 2^e - hi)
-// (representation error <= 2^-23 |x| for entries within 2^-18 of the maximum, <= 2^-40 max|x| absolute below that;
-// tools/fp16_split_experiment.py, profiles/r01_fp16_split_experiment.md).  The epilogue multiplies the accumulator by
-// 2^-(ea + eb); the scaling is exact, so it changes nothing but the representable range.
-__host__ __device__ __forceinline__ int scale_exp(float amax) {
-  int e;
-  frexpf(amax * 1.00001f, &e);          // amax * 1.00001 < 2^e
-  return 15 - e;
-}
-__device__ __forceinline__ int kx_exp(float amp2) { return scale_exp(amp2 * 1.000001f); }   // cross-covariance <= amp2 (1 + 1e-6)
-__device__ __forceinline__ void split16(float x, __half& h, __half& l) {
-  h = __float2half_rn(x);
-  l = __float2half_rn(x - __half2float(h));
-}
-__device__ __forceinline__ uint2 pack4(const __half (&v)[4]) {
-  __half2 a = __halves2half2(v[0], v[1]), b = __halves2half2(v[2], v[3]);
-  uint2 r;
-  r.x = *reinterpret_cast<unsigned*>(&a);
-  r.y = *reinterpret_cast<unsigned*>(&b);
-  return r;
-}
-
 // max |hi + lo| per sample (bits of a non-negative float order like unsigned integers)
 __global__ void __launch_bounds__(256) linv_absmax_kernel(long per4, const float4* __restrict__ hi,
                                                           const float4* __restrict__ lo, unsigned* __restrict__ maxbits) {
@@ -268,36 +243,6 @@ __global__ void alpha_pack_f16_kernel(int N, int Np, int F, int Fp, int Npad_alp
 // Kxt[s][c][n] * 2^ea as an fp16 (hi, lo) pair (two 8-byte stores per 4 values, 128 B contiguous per 16 threads),
 // ea = scale_exp(amp2[s] (1 + 1e-6));  mu[s][c] = sum_n alpha[n] Kx[c][n] + mean.   grid = (Mc/128, S).
 // 4 B written per (3D + 25) flops.
-// Fast stationary kernels for the generator (float32): sqrt.approx / ex2.approx (MUFU, ~1-2 ulp) instead of the accurate
-// sqrtf/expf sequences -- their relative error (~2e-7) is at the level of the float32 rounding already carried by r2.
-// The kernel is issue-bound (ncu r01: 110 instructions per element, 73% issue-slot utilisation, FMA pipe 53%), so the
-// arithmetic is written with Blackwell's packed float32 instructions (FADD2 / FFMA2 / FMUL2: two lanes per issue slot).
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {
-  float y;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
-__device__ __forceinline__ float2 kernel_pair_fast(int kind, float2 r2) {
-  constexpr float kL2E = 1.4426950408889634f;
-  if (kind <= 1) {                                            // SE / ARDSE: exp(-r2 / 2)
-    const float2 t = __fmul2_rn(r2, dup2(-0.5f * kL2E));
-    return make_float2(ex2_approx(t.x), ex2_approx(t.y));
-  }
-  const float2 r = make_float2(sqrt_approx(r2.x), sqrt_approx(r2.y));
-  const float c = (kind == 2) ? 1.7320508075688772f : 2.23606797749979f;
-  const float2 t = __fmul2_rn(r, dup2(-c * kL2E));
-  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-  float2 p = __ffma2_rn(r, dup2(c), dup2(1.f));               // Matern32: (1 + sqrt3 r) e^-sqrt3 r
-  if (kind == 3) p = __ffma2_rn(r2, dup2(5.0f / 3.0f), p);    // Matern52: (1 + sqrt5 r + 5/3 r2) e^-sqrt5 r
-  return __fmul2_rn(p, e);
-}
-
 constexpr int kKD = 16;   // D chunk staged in shared memory (25 KB total)
 
 __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, int M, int c_begin, int Mc, int D,
@@ -431,36 +376,6 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both oper
 constexpr int THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                            uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
-      : "memory");
-}
 // K-major swizzled operand tile: rows of ROW_BYTES, 8-row swizzle atoms (SBO = 8 rows), LBO unused (=1).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -492,22 +407,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(kIdescF16), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-
 struct Args {
   int S, Np, Mc, ntiles, npairs, ngroups, ldp;   // Mc = candidates per chunk (multiple of 128); ldp = partial stride
   float* partial;                                 // [npairs][S][ldp]
@@ -767,14 +666,34 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
   }
 }
 
+// var = amp2 (1 + 1e-6) - sum_p partial[p]; with the tensor-core generator also mu = amp2 * sum_j mu_partial[j] + mean
 __global__ void finish_var_kernel(int M, int c_begin, int Mc, int S, int npairs, int ldp, const float* __restrict__ partial,
-                                  const float* __restrict__ amp2, float* __restrict__ var, int ldm) {
+                                  const float* __restrict__ amp2, float* __restrict__ var, int ldm, int nmp,
+                                  const float* __restrict__ mu_partial, const float* __restrict__ mean,
+                                  float* __restrict__ mu) {
   int c = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
   if (c >= Mc || c_begin + c >= M) return;
   float t = 0.f;
   for (int pr = 0; pr < npairs; ++pr) t += partial[((long)pr * S + s) * ldp + c];
   var[(long)s * ldm + c_begin + c] = amp2[s] * 1.000001f - t;
+  if (nmp > 0) {
+    float m = 0.f;
+    for (int j = 0; j < nmp; ++j) m += mu_partial[((long)j * S + s) * ldp + c];
+    mu[(long)s * ldm + c_begin + c] = fmaf(amp2[s], m, mean[s]);
+  }
 }
+
+}  // namespace tc
+__global__ void kxt_mu_finish_kernel(int M, int Mc, int S, int nmp, const float* __restrict__ mu_partial,
+                                     const float* __restrict__ amp2, const float* __restrict__ mean,
+                                     float* __restrict__ mu, int ldm) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  if (c >= M) return;
+  float m = 0.f;
+  for (int j = 0; j < nmp; ++j) m += mu_partial[((long)j * S + s) * Mc + c];
+  mu[(long)s * ldm + c] = fmaf(amp2[s], m, mean[s]);
+}
+namespace tc {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -819,6 +738,15 @@ static int make_map_h(CUtensorMap* m, const __half* ptr, uint64_t rows, uint64_t
 }  // namespace tc
 
 int num_sms();
+// tensor-core cross-covariance generator (kxt_tc.cu)
+bool kxt_tc_supported(int D, int S);
+int kxt_tc_ngroups(int Np);
+size_t kxt_tc_workspace_bytes(int Np, int Mc, int S, int M, int D);
+int kxt_tc_prepare(void* ws, int N, int Np, int M, int Mc, int D, int S, const float* X, const float* Cc, cudaStream_t st);
+int kxt_tc(void* ws, int kind, int N, int Np, int M, int c_begin, int Mc, int mc_used, int D, int S, const float* inv_ls,
+           const float* amp2, const float* alpha, int Npad_alpha, __half* khi, __half* klo, cudaStream_t st);
+float* kxt_tc_mu_partial(void* ws, int Np, int Mc, int S, int M, int D);
+static const int kKxtWsD = 32;     // the generator workspace is sized for its largest supported dimension
 
 // ---------------------------------------------------------------------------------------------------- host side
 int tc_np(int N) { return ((N + tc::BN - 1) / tc::BN) * tc::BN; }
@@ -1047,7 +975,41 @@ size_t predict_tc_workspace_bytes(int Np, int M, int S, int F) {
   size_t mc = tc_chunk_cands(Np, M, S, kTcBudget);
   int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2, nbuf = tc_nbuf(Np, M, S, kTcBudget);
   return (size_t)nbuf * S * mc * Np * 2 * sizeof(__half) + (size_t)npairs * S * mc * sizeof(float) +
-         2 * (size_t)S * fant_rows(F) * Np * sizeof(__half) + (size_t)S * sizeof(int) + 1024;
+         2 * (size_t)S * fant_rows(F) * Np * sizeof(__half) + (size_t)S * sizeof(int) + 1024 +
+         kxt_tc_workspace_bytes(Np, (int)mc, S, M, kKxtWsD);
+}
+
+// Generator only (one chunk, Mc = ceil128(M)): khi/klo [S][Mc][Np] halves, mu [S][ldm].  impl: 0 = packed SIMT kernel,
+// 1 = tensor-core kernel.  Used by the tests to compare the two implementations element by element.
+size_t kxt_pack_workspace_bytes(int Np, int M, int S) {
+  return kxt_tc_workspace_bytes(Np, ((M + 127) / 128) * 128, S, M, kKxtWsD) + 256;
+}
+int kxt_pack(int impl, int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
+             const float* amp2, const float* mean, const float* alpha, int Npad_alpha, __half* khi, __half* klo,
+             float* mu, int ldm, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (kind < 0 || kind > 3) return -2;
+  if (N <= 0 || Np < N || Np % tc::BN) return -4;
+  if (M <= 0 || D <= 0 || S <= 0) return -5;
+  if (!X || !Cc || !inv_ls || !amp2 || !mean || !alpha || !khi || !klo || !mu) return -8;
+  if (ldm < M) return -18;
+  const int Mc = ((M + 127) / 128) * 128;
+  if (impl == 0) {
+    kxt_kernel<<<dim3(Mc / 128, S), 256, 0, st>>>(kind, N, Np, M, 0, Mc, D, X, Cc, inv_ls, amp2, mean, alpha, Npad_alpha,
+                                                  khi, klo, mu, ldm);
+    count_launch();
+    return check_launch("kxt_pack");
+  }
+  if (!kxt_tc_supported(D, S)) return -1;
+  if (!workspace || workspace_bytes < kxt_pack_workspace_bytes(Np, M, S)) return -20;
+  const int nmp = kxt_tc_ngroups(Np);
+  int rc = kxt_tc_prepare(workspace, N, Np, M, Mc, D, S, X, Cc, st);
+  if (rc) return rc;
+  rc = kxt_tc(workspace, kind, N, Np, M, 0, Mc, Mc, D, S, inv_ls, amp2, alpha, Npad_alpha, khi, klo, st);
+  if (rc) return rc;
+  float* mu_partial = kxt_tc_mu_partial(workspace, Np, Mc, S, M, D);
+  kxt_mu_finish_kernel<<<dim3((Mc + 255) / 256, S), 256, 0, st>>>(M, Mc, S, nmp, mu_partial, amp2, mean, mu, ldm);
+  count_launch();
+  return check_launch("kxt_pack");
 }
 
 int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
@@ -1074,6 +1036,18 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   __half* ahi = reinterpret_cast<__half*>(partial + (size_t)npairs * S * Mc);   // alpha^T hi | lo  [S][Fp][Np]
   __half* alo = ahi + (size_t)S * Fp * Np;
   int* fexp = reinterpret_cast<int*>(alo + (size_t)S * Fp * Np);
+  // generator: the packed-float32 SIMT kernel is the production path (62-70 ms at the headline); the tensor-core
+  // generator of kxt_tc.cu is parity-complete but request-bound on its output path (148 ms) and opt-in: SMK_KXT_IMPL=tc
+  static int gen_env = -1;
+  if (gen_env < 0) { const char* e = getenv("SMK_KXT_IMPL"); gen_env = (e && !strcmp(e, "tc")) ? 1 : 0; }
+  const bool gen_tc = gen_env == 1 && kxt_tc_supported(D, S) && nbuf == 1;
+  const int nmp = gen_tc ? kxt_tc_ngroups(Np) : 0;
+  void* kws = reinterpret_cast<void*>(fexp + S);
+  float* mu_partial = gen_tc ? kxt_tc_mu_partial(kws, Np, Mc, S, M, D) : nullptr;
+  if (gen_tc) {
+    int rc = kxt_tc_prepare(kws, N, Np, M, Mc, D, S, X, Cc, st);
+    if (rc) return rc;
+  }
   CUtensorMap mFhi, mFlo;
   if (fant) {
     const long total = (long)S * Fp * Np;
@@ -1124,8 +1098,13 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     const int mc_used = min(Mc, ((M - c_begin) + 127) / 128 * 128);
     if (overlap && ci >= 2) cudaStreamWaitEvent(aux, ev_mma[b], 0);      // buffer b is free again
     timing_begin("kxt_kernel", kst);
-    kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, kst>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
-                                                        alpha, Npad_alpha, kh, kh + kelems, mu, ldm);
+    if (gen_tc) {
+      int rc = kxt_tc(kws, kind, N, Np, M, c_begin, Mc, mc_used, D, S, inv_ls, amp2, alpha, Npad_alpha, kh, kh + kelems, kst);
+      if (rc) return rc;
+    } else {
+      kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, kst>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
+                                                          alpha, Npad_alpha, kh, kh + kelems, mu, ldm);
+    }
     timing_end(kst);
     if (overlap) {
       cudaEventRecord(ev_kxt[b], aux);
@@ -1144,7 +1123,7 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi[b], mAlo[b], mBhi, mBlo, a);
     timing_end(st);
     tc::finish_var_kernel<<<dim3((mc_used + 255) / 256, S), 256, 0, st>>>(M, c_begin, mc_used, S, npairs, Mc, partial,
-                                                                        amp2, var, ldm);
+                                                                        amp2, var, ldm, nmp, mu_partial, mean, mu);
     count_launch(3);
     if (fant) {      // fantasy means: same Kxt chunk against alpha^T, rectangular k range (OPT:609)
       tc::Args r = a;

@@ -262,3 +262,65 @@ def test_predict_tc_operand_scaling_range(engines, amp2, noise):
         m_ref, v_ref, _, _ = O.predict("Matern52", h, X, Cd, y)
         np.testing.assert_allclose(var[s, :M], v_ref, rtol=1e-3, atol=3e-4 * h[2])
         np.testing.assert_allclose(mu[s, :M], m_ref, rtol=1e-4, atol=1e-3 * np.sqrt(amp2))
+
+
+# ---------------------------------------------------------------------------------- cross-covariance operand generators
+def _kxt_pack(eng, impl, kind, X, Cd, hs, alpha_np):
+    """Runs one generator (0 = packed SIMT, 1 = tensor core) and returns (K [S][M][N] float64, mu [S][M])."""
+    import torch
+    from spearmint_b200 import _lib
+    from spearmint_b200.engine import ptr, check, KINDS as KCODE
+    L = _lib.lib()
+    hb = eng.hypers(hs, kind)
+    N, D = X.shape
+    M, S = Cd.shape[0], hb.S
+    Np, Mc, ldm = L.smk_tc_np(N), ((M + 127) // 128) * 128, ((M + 127) // 128) * 128
+    Xd, Cdev = eng.to_dev(X), eng.to_dev(Cd)
+    alpha = torch.zeros((S, Np), dtype=torch.float32, device=eng.device)
+    alpha[:, :N] = torch.from_numpy(alpha_np.astype(np.float32)).to(eng.device)
+    h16 = torch.full((S, Mc, Np), float("nan"), dtype=torch.float16, device=eng.device)
+    l16 = torch.full((S, Mc, Np), float("nan"), dtype=torch.float16, device=eng.device)
+    mu = torch.zeros((S, ldm), dtype=torch.float32, device=eng.device)
+    nb = L.smk_kxt_pack_workspace_bytes(Np, M, S)
+    ws = torch.empty((nb,), dtype=torch.uint8, device=eng.device)
+    rc = L.smk_kxt_pack_f16(impl, KCODE[kind], N, Np, M, D, S, ptr(Xd), ptr(Cdev), ptr(hb.inv_ls), ptr(hb.amp2),
+                            ptr(hb.mean), ptr(alpha), Np, ptr(h16), ptr(l16), ptr(mu), ldm, ptr(ws), nb, eng.stream())
+    if rc == -1:
+        return None, None
+    check(rc, "kxt_pack")
+    torch.cuda.synchronize()
+    ea = np.array([15 - np.frexp(np.float32(np.float32(h[2]) * np.float32(1.000001)) * np.float32(1.00001))[1] for h in hs])
+    K = (h16.double() + l16.double()).cpu().numpy() * (2.0 ** -ea)[:, None, None]
+    return K, mu.double().cpu().numpy()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("D,N,M,S", [(32, 300, 200, 5), (8, 520, 257, 10), (1, 100, 64, 2), (3, 1000, 130, 40), (17, 129, 128, 33)])
+def test_kxt_generators_match_oracle(engines, kind, D, N, M, S):
+    """Both generator implementations against the float64 cross-covariance: every element of the operand (incl. zero
+    padding of the observation axis) and the fused mean."""
+    eng = engines["f32"]
+    X, Cd, y, hs = _problem(D, N, M, S, 3)
+    Cd[:5] = X[0] + 1e-3 * np.random.RandomState(0).randn(5, D)          # the jitter cloud around an observation
+    rs = np.random.RandomState(4)
+    alpha = rs.randn(S, N) * 3.0
+    for impl in (0, 1):
+        K, mu = _kxt_pack(eng, impl, kind, X, Cd, hs, alpha)
+        assert K is not None
+        assert np.isfinite(K[:, :M]).all()
+        assert np.all(K[:, :M, N:] == 0)
+        for s, h in enumerate(hs):
+            Kref = O.cov(kind, h[2], h[3], X, Cd).T                       # (M, N)
+            err = np.abs(K[s, :M, :N] - Kref).max()
+            assert err <= 3e-6 * h[2], (impl, s, err)
+            mref = Kref @ alpha[s] + h[0]
+            np.testing.assert_allclose(mu[s, :M], mref, rtol=2e-5, atol=2e-5 * np.abs(Kref * alpha[s]).sum(1).max())
+
+
+def test_kxt_tc_generator_declines_unsupported_shapes(engines):
+    eng = engines["f32"]
+    X, Cd, y, hs = _problem(40, 64, 64, 2, 3)
+    K, _ = _kxt_pack(eng, 1, "Matern52", X, Cd, hs, np.zeros((2, 64)))
+    assert K is None                                                      # D > 32: the SIMT generator handles it
+    K, _ = _kxt_pack(eng, 0, "Matern52", X, Cd, hs, np.zeros((2, 64)))
+    assert K is not None
