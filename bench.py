@@ -322,7 +322,7 @@ def run_b200_arm(args, D, N, M, S):
                 else "smk::predict_kernel<float> (SIMT FMA)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": (achieved / pk["tensor_sustained"]) if achieved else None,
-                "traffic": ncu_traffic(args.workload, impl, world, M, n_launch_step),
+                "traffic": ncu_traffic(args.workload, impl, world, M, n_launch_step) if Sl == 40 else None,
                 "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": alg / n_launch_step, "launches_per_step": n_launch_step,
                 "kernel_ms_per_launch": kms_step / n_launch_step, "kernel_ms_per_step": kms_step,

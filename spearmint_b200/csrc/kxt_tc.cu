@@ -48,13 +48,14 @@ namespace ktc {
 using namespace tc;
 
 constexpr int TN = 128;            // observations per tile (MMA N, TMEM columns per buffer)
-constexpr int BSTAGES = 3;         // B-operand (q tile) stages
+constexpr int BSTAGES = 2;         // B-operand (q tile) stages
 constexpr int TBUF = 4;            // TMEM accumulator buffers (4 x 128 columns)
 constexpr int NGRP = 3;            // epilogue groups
 constexpr int MAXD = 32;           // padded dimension limit
 constexpr int MAXK = 96;           // J * Dp limit: one q stage = 128 x 96 halves x (hi, lo) = 48 KB
 constexpr int MAXS = 128;          // one sample per TMEM lane
 constexpr int THREADS = 16 * 32;
+constexpr int ALD = TN + 4;        // row length (floats) of the staged alpha tile: 528-byte stride -> conflict-free row reads
 
 struct Args {
   int kind, N, Np, M, c_begin, Mc, D, Dp, S, J, K, Npad_alpha;
@@ -69,13 +70,28 @@ struct Args {
 
 __host__ __device__ inline int slots(int S, int Dp) { int j = 128 / S, k = MAXK / Dp; return j < k ? j : k; }
 
-__host__ __device__ inline size_t smem_bytes(int K) {
-  return (size_t)BSTAGES * 2 * TN * K * 2 + (size_t)2 * 128 * K * 2 + MAXK * 4 /*candidate rows*/ + 256 /*barriers*/ +
-         128 /*align*/;
+__host__ __device__ inline size_t smem_bytes(int K, int S) {
+  return (size_t)BSTAGES * 2 * TN * K * 2 + (size_t)2 * 128 * K * 2 + MAXK * 4 /*candidate rows*/ +
+         (size_t)NGRP * S * ALD * 4 /*alpha tiles*/ + 256 /*barriers*/ + 1024 /*align*/;
 }
 
-// K-major, no swizzle: element (row r, 16-byte k block j) of a tile with C k-blocks per row
-__device__ __forceinline__ uint32_t core_off(int r, int j, int C) { return (uint32_t)((((r >> 3) * C + j) << 7) + ((r & 7) << 4)); }
+// Operand tiles are K-major with the 64-byte swizzle (one candidate slot = 32 halves = one 64-byte row), stored as
+// J blocks of [128 rows x 64 B]; the 16-byte chunk c of row r sits at chunk (c ^ ((r >> 1) & 3)) -- Swizzle<2,4,3> on
+// byte addresses, the pattern TMA produces for CU_TENSOR_MAP_SWIZZLE_64B and tcgen05.mma expects for layout type 4.
+// (A first version used the no-swizzle core-matrix layout: numerically fine, but each 128x128x16 MMA then took ~1600
+// cycles -- the tensor pipe was 4.9 % active while every other warp waited for it; ncu, profiles/r01_kxt_tc_ncu.md.)
+constexpr uint32_t SLOT_BYTES = 128 * 64;
+__device__ __forceinline__ uint32_t core_off(int r, int jbg, int /*C*/) {
+  return (uint32_t)(jbg >> 2) * SLOT_BYTES + (uint32_t)r * 64u + (uint32_t)(((jbg & 3) ^ ((r >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;                         // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                                  // SWIZZLE_64B
+  return d;
+}
 
 __device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -99,14 +115,15 @@ __device__ __forceinline__ unsigned h2_bits(__half2 h) { return *reinterpret_cas
 
 __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  const int Dp = p.Dp, K = p.K, C = K >> 3, CD = Dp >> 3;   // 16-byte k blocks per operand row / per candidate slot
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int Dp = p.Dp, K = p.K, C = K >> 3, CD = Dp >> 3;   // 16-byte k blocks per operand row / per candidate slot (4)
   const uint32_t BH = (uint32_t)TN * K * 2;          // bytes of one B half (hi or lo)
   const uint32_t WH = (uint32_t)128 * K * 2;
   unsigned char* sB = base;
   unsigned char* sW = sB + (size_t)BSTAGES * 2 * BH;
   float* cs = reinterpret_cast<float*>(sW + 2 * WH);             // [J][Dp] candidate rows of the current item
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cs + MAXK);
+  float* sAl = cs + MAXK;                                        // [NGRP][S][ALD] alpha tile of each epilogue group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAl + (size_t)NGRP * p.S * ALD);
   uint64_t* b_full = bars;
   uint64_t* b_empty = b_full + BSTAGES;
   uint64_t* t_full = b_empty + BSTAGES;
@@ -172,8 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
     // ahead (a first version with serial rounds of dependent loads per (row, slot) unit was latency-bound: 21 us per
     // tile); the J candidate rows of the item sit in shared memory.  Lane 0 of warp 3 also issues the MMAs of the tile.
     const int r = tid;
-    const uint32_t lbo = 128u, sbo = (uint32_t)C * 128u;
-    const uint64_t whi = desc_nosw(smem_u32(sW), lbo, sbo), wlo = desc_nosw(smem_u32(sW + WH), lbo, sbo);
+    const uint64_t whi = desc_sw64(smem_u32(sW)), wlo = desc_sw64(smem_u32(sW + WH));
     const int ksteps = K / 16;
     float4 xc[MAXD / 4], xn[MAXD / 4];
 #pragma unroll
@@ -231,9 +247,9 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d = tmem_base + (uint32_t)b * TN;
           const uint32_t sb = smem_u32(bh);
-          const uint64_t bhi = desc_nosw(sb, lbo, sbo), blo = desc_nosw(sb + BH, lbo, sbo);
+          const uint64_t bhi = desc_sw64(sb), blo = desc_sw64(sb + BH);
           for (int q = 0; q < ksteps; ++q) {
-            const uint64_t ko = (uint64_t)((q * 256) >> 4);            // 16 halves = 2 k blocks of 128 B
+            const uint64_t ko = (uint64_t)(((q >> 1) * SLOT_BYTES + (q & 1) * 32) >> 4);   // slot block, then 32 B inside the row
             umma_f16(d, wlo + ko, bhi + ko, q ? 1u : 0u);              // small terms first
             umma_f16(d, whi + ko, blo + ko, 1u);
             umma_f16(d, whi + ko, bhi + ko, 1u);
@@ -262,7 +278,10 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
     }
     const float2 scl2 = dup2(scl);
     const float2 a2s = dup2(a2 * ldexpf(1.f, kx_exp(a2)));
-    const float* al_row = p.alpha + (size_t)(row_used ? s : 0) * p.Npad_alpha;
+    float* gal = sAl + (size_t)grp * p.S * ALD;      // this group's alpha tile [S][ALD]
+    const float* al_row = gal + (size_t)(row_used ? s : 0) * ALD;
+    const int gt = tid - 128 - grp * 128;             // thread index inside the group (0..127)
+    const int bar_id = 2 + grp;
     long t = 0;
     for (long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int crow = (int)item * p.J + j;           // candidate row inside the chunk
@@ -274,6 +293,18 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         const int b = (int)(t % TBUF);
         const int n0 = nb * TN;
         const bool edge = n0 + TN > p.N;
+        // alpha_s[n0 .. n0+127] for all samples -> shared memory with coalesced 512-byte row reads (read per lane straight
+        // from global they were 30 sectors per request and 80 % of all stall samples: ncu r01, profiles/r01_kxt_tc_ncu.md)
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // previous tile's readers are done
+        for (int f = gt; f < p.S * (TN / 4); f += 128) {
+          const int rs = f >> 5, c4 = (f & 31) * 4, n = n0 + c4;
+          const float* src = p.alpha + (size_t)rs * p.Npad_alpha + n;
+          float4 a4;
+          if (n + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(src));
+          else a4 = make_float4(n < p.N ? src[0] : 0.f, n + 1 < p.N ? src[1] : 0.f, n + 2 < p.N ? src[2] : 0.f, 0.f);
+          *reinterpret_cast<float4*>(gal + (size_t)rs * ALD + c4) = a4;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         mbar_wait(&t_full[b], (uint32_t)((t / TBUF) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)b * TN;
@@ -281,16 +312,6 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         for (int cq = 0; cq < TN; cq += 32) {
           uint32_t r[32];
           tmem_ld32(t0 + cq, r);
-          float4 al[8];
-          if (act) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int n = n0 + cq + 4 * k;
-              al[k] = (n + 3 < p.N) ? __ldg(reinterpret_cast<const float4*>(al_row + n))
-                                    : make_float4(n < p.N ? al_row[n] : 0.f, n + 1 < p.N ? al_row[n + 1] : 0.f,
-                                                  n + 2 < p.N ? al_row[n + 2] : 0.f, 0.f);
-            }
-          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (act) {
 #pragma unroll
@@ -308,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
                   if (n >= p.N) kk.x = 0.f;
                   if (n + 1 >= p.N) kk.y = 0.f;
                 }
-                const float4 a4 = al[(col >> 2)];
+                const float4 a4 = *reinterpret_cast<const float4*>(al_row + cq + (col & ~3));
                 const float2 ap = (col & 2) ? make_float2(a4.z, a4.w) : make_float2(a4.x, a4.y);
                 v = __ffma2_rn(kk, ap, v);
                 const float2 val = __fmul2_rn(kk, a2s);
@@ -365,11 +386,15 @@ __global__ void __launch_bounds__(256) kxt_prep_kernel(long rows_out, int rows, 
 }  // namespace ktc
 
 // ---------------------------------------------------------------------------------------------------- host side
-bool kxt_tc_supported(int D, int S) { return D <= ktc::MAXD && S <= ktc::MAXS; }
+bool kxt_tc_supported(int D, int S) {
+  if (D > ktc::MAXD || S > ktc::MAXS) return false;
+  const int Dp = ktc::MAXD;
+  return ktc::smem_bytes(ktc::slots(S, Dp) * Dp, S) <= (size_t)227 * 1024;
+}
 
 int kxt_tc_ngroups(int) { return ktc::NGRP; }       // mean partial planes per chunk
 
-static int kxt_dp(int D) { return ((D + 15) / 16) * 16; }
+static int kxt_dp(int) { return ktc::MAXD; }         // one candidate slot = one 64-byte swizzle row (32 halves)
 static size_t kxt_cp_rows(int M) { return (size_t)((M + 127) / 128) * 128 + 128; }   // chunk tail + J slack, clamped copies
 
 // workspace: mean partials of one chunk | padded scaled coordinates of X and of all candidates | range words
@@ -422,11 +447,11 @@ int kxt_tc(void* ws, int kind, int N, int Np, int M, int c_begin, int Mc, int mc
   a.nitems = (mc_used + a.J - 1) / a.J;
   a.Xp = pl.Xp; a.Cp = pl.Cp; a.inv_ls = inv_ls; a.amp2 = amp2; a.alpha = alpha; a.qmax = pl.qmax;
   a.khi = khi; a.klo = klo; a.mu_partial = pl.mu_partial;
-  const size_t smem = ktc::smem_bytes(a.K);
+  const size_t smem = ktc::smem_bytes(a.K, S);
   const int grid = (int)std::min<long>(a.nitems, num_sms());
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(ktc::kxt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ktc::smem_bytes(ktc::MAXK));
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   ktc::kxt_tc_kernel<<<grid, ktc::THREADS, smem, st>>>(a);
