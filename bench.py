@@ -205,6 +205,9 @@ def run_b200_arm(args, D, N, M, S):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: the product arm needs a CUDA device (B200, sm_100a) -- there is no CPU fallback; "
+                         "the CPU arm is `--impl reference`")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))

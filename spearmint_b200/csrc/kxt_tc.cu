@@ -22,13 +22,15 @@
 // STATUS (round 1): numerically complete and parity-tested against the float64 oracle (tests/test_gpu_kernels.py::
 // test_kxt_generators_match_oracle), but NOT the production generator: with lane = (candidate, sample) every warp-level
 // 16-byte load of alpha and 16-byte store of the operand touches 32 different rows, i.e. ~8e9 separate L2 requests per
-// headline step against ~5e8 for the SIMT kernel's 128-byte-contiguous stores -- 148 ms vs 62-70 ms.  The fix is an
-// output path through shared memory + TMA tensor stores (and a TMA-staged alpha tile); until then predict_tc() uses the
-// packed-float32 SIMT generator and this kernel is opt-in (SMK_KXT_IMPL=tc).
+// headline step against ~5e8 for the SIMT kernel's 128-byte-contiguous stores -- 144-148 ms vs 62-70 ms.  ncu (profiles/
+// r01_kxt_tc_ncu.md) shows nothing bandwidth-bound: the epilogue warps are starved for finished accumulators (358 M spins
+// on the accumulator barrier per launch) while tensor pipe, issue slots and L2 idle; staging alpha in shared memory, the
+// swizzled operand layout and restructured producers were each tried and are not the limiter.  Until the hand-off stall is
+// found predict_tc() uses the packed-float32 SIMT generator and this kernel is opt-in (SMK_KXT_IMPL=tc).
 //
 // Roles in a CTA of 16 warps:  warps 0-3 producers (thread = observation row: q for the J candidate slots -> fp16 (hi, lo)
-// -> shared memory, canonical K-major no-swizzle core-matrix layout: (8 rows x 16 B) blocks, LBO = next k block, SBO =
-// next 8 rows; lane 0 of warp 3 also issues the tile's MMAs; warp 3 owns the TMEM allocation);  warps 4-15 three epilogue
+// -> shared memory in the 64-byte-swizzled K-major layout, one [128 x 64 B] block per candidate slot; lane 0 of warp 3 also
+// issues the tile's MMAs; warp 3 owns the TMEM allocation);  warps 4-15 three epilogue
 // groups (tile t -> group t mod 3), 4 TMEM buffers of 128 columns.  Work item = J candidates x all observations.
 #include <cuda_fp16.h>
 #include <cuda.h>
@@ -93,13 +95,6 @@ __device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell); layout type 0 = no swizzle
-  return d;
-}
 // kind::f16, f16 x f16 -> f32, both operands K-major, M = 128, N = 128
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {

@@ -1,20 +1,27 @@
-// predict_tc.cu -- tensor-core (tcgen05 / TMEM / TMA) version of the fused predict stage.
+// predict_tc.cu -- tensor-core (tcgen05 / TMEM / TMA) version of the fused predict stage, and the tensor-core variants
+// of the two N^3 factor steps that share its kernel.
 //
 // Same contract as predict.cu (reference spans OPT:536, 544, 547-548), different dataflow:
-//   1. trtri   : Linv = L^-1 (explicit, blocked, float32 SIMT) -- removes the row-block dependency chain of the
-//                triangular solve so that  beta = Linv * Kx  is one dense (lower-trapezoidal) contraction.
-//   2. split   : Linv -> (hi, lo) with hi = tf32-truncated value, lo = x - hi   (exact in float32)
-//   3. kxt     : Kxt[s][c][n] = amp2 k(X_n, C_c) for a chunk of candidates, written candidate-major (n contiguous,
-//                i.e. K-major for the MMA) already split into (hi, lo); fused  mu[c] = sum_n alpha[n] Kx[c][n] + mean.
+//   1. trtri   : Linv = L^-1 explicitly (row-block recurrence on tcgen05, mode 3; SIMT version for small N) -- removes the
+//                row-block dependency chain of the triangular solve: beta = Linv * Kx is one dense (lower-trapezoidal)
+//                contraction.  Kept as a tf32 (hi, lo) pair of float arrays (hi = x & 0xffffe000, lo = x - hi).
+//   2. pack    : GEMM-operand copy of Linv: per-sample power-of-two scale 2^eb (largest |entry| -> [2^14, 2^15)) and the
+//                round-to-nearest fp16 (hi, lo) pair (linv_pack_f16).
+//   3. kxt     : Kxt[s][c][n] = amp2 k(X_n, C_c) * 2^ea for a chunk of candidates, candidate-major (n contiguous, i.e.
+//                K-major for the MMA) as an fp16 (hi, lo) pair; fused mu[c] = sum_n alpha[n] Kx[c][n] + mean.
+//                (kxt_kernel below: packed-float32 SIMT; kxt_tc.cu: opt-in tensor-core generator.)
 //   4. mma     : per (sample, 128-candidate tile, row-group pair):  D[c][i] = sum_n Kxt[c][n] * Linv[i][n]
-//                as 3xTF32  (hi*hi + hi*lo + lo*hi)  with tcgen05.mma.kind::tf32, operands staged by TMA
-//                (128B swizzle), accumulators in TMEM (2 x 256 columns, double-buffered against the epilogue);
-//                epilogue = tcgen05.ld + per-lane sum of squares (one candidate per TMEM lane: no cross-thread
-//                reduction), partial sums per row-group pair.
+//                as 3 x FP16 (lo*hi + hi*lo + hi*hi) with tcgen05.mma.kind::f16, fp32 accumulation, operands staged by
+//                TMA (64-byte swizzle, 4 stages), accumulators in TMEM (2 x 256 columns, double-buffered against the
+//                epilogue); epilogue = tcgen05.ld, un-scale by 2^-(ea+eb), per-lane sum of squares (one candidate per
+//                TMEM lane: no cross-thread reduction), partial sums per row-group pair.
 //   5. finish  : var = amp2 (1 + 1e-6) - sum_p partial[p]
-// Why 3xTF32: a single TF32 pass (10-bit mantissa) cannot resolve var = amp2 - |beta|^2 (it goes negative on the
-// reference's own test problems); hi/lo splitting restores ~2^-21 operand accuracy at 3 MMAs
-// per product, i.e. 1/6 of the dense bf16 tensor peak is the ceiling of this formulation.
+// Why a split at all: a single TF32/FP16 pass (11-bit significand) cannot resolve var = amp2 - |beta|^2 (it goes negative
+// on the reference's own test problems).  Why fp16 rather than tf32 halves: same significand, twice the tensor rate; the
+// missing exponent range is supplied by the exact scaling.  3 MMAs per product => 1/3 of the dense
+// bf16 tensor peak is the ceiling of this formulation; the kernel runs the tensor pipe 98.8 % active.
+// Modes 2 (Cholesky update) and 3 (triangular inverse) of the same kernel keep tf32 (hi, lo) operands: they are produced
+// block by block, before a global scale is known.
 #include <cuda_fp16.h>
 #include <cuda.h>
 
@@ -506,6 +513,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
       // A (cross-covariance slab of one candidate tile, 2 MB) is read by the 8 row-group-pair CTAs of that tile at
       // different times: EVICT_FIRST made 7 of the 8 reads come from HBM (ncu r01: 103 GB read per launch vs 24 GB
       // algorithmic); mode 0 therefore keeps it under the normal policy.  Modes 2/3 stream A once.
+      // (SMK_TC_A_EVICT_FIRST=1 restores the old hint for A/B measurements.)
       const uint64_t hintA = (p.mode == 0 && !p.a_evict_first) ? 0x1000000000000000ull : 0x12F0000000000000ull;   // EVICT_NORMAL : EVICT_FIRST
       const uint64_t hintB = 0x14F0000000000000ull;   // EVICT_LAST : the B operand is re-read by many items
       int stage = 0;

@@ -218,7 +218,7 @@ def test_predict_tc_beta_and_moments(engines, D, N, M):
     exps = exps.cpu().numpy()[:hb.S]
     for s in range(hb.S):       # exact power-of-two scale into [2^14, 2^15), hi + lo reproduces the float32 inverse to 2^-21
         sc = np.abs(linv[s]).max() * 2.0 ** exps[s]
-        assert 2.0 ** 14 <= sc < 2.0 ** 15, (sc, exps[s])
+        assert 2.0 ** 14 / 1.0001 <= sc < 2.0 ** 15, (sc, exps[s])     # (the 1.00001 safety factor can land just below 2^14)
         rec = (h16[s].double() + l16[s].double()).cpu().numpy() * 2.0 ** -float(exps[s])
         assert np.abs(rec - linv[s]).max() <= 2.0 ** -21 * np.abs(linv[s]).max()
         big = np.abs(linv[s]) >= 2.0 ** -17 * np.abs(linv[s]).max()
