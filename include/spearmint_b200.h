@@ -145,6 +145,10 @@ size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F);
  * amp2 (1 + 1e-6) 1.00001));  mu: [S][ldm].  impl 0: packed-float32 SIMT kernel (any D, S); impl 1: tensor-core kernel
  * (q = (x - c)^2 once per pair, contraction over dimensions for all samples on tcgen05; D <= 32, S <= 64, else -1).  */
 size_t smk_kxt_pack_workspace_bytes(int Np, int M, int S);
+/* debug only: clock64() stamps of the first 64 tiles of CTA 0 of the last impl-1 launch made with SMK_KXT_TIMELINE=1
+ * ([tile][8]: production start / end, issuer arrives / operands+accumulator ready / committed, epilogue waits / accumulator
+ * ready / drained); out: host memory. */
+int smk_debug_kxt_tc_timeline(long long* out, int n);
 int smk_kxt_pack_f16(int impl, int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
                      const float* inv_ls, const float* amp2, const float* mean, const float* alpha, int Npad_alpha,
                      void* k_h16, void* k_l16, float* mu, int ldm, void* workspace, size_t workspace_bytes, void* stream);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "smk_trtri_split_tc_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "smk_linv_alpha_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p], _i),
     "smk_kxt_pack_workspace_bytes": ([_i, _i, _i], _sz),
+    "smk_debug_kxt_tc_timeline": ([_p, _i], _i),
     "smk_kxt_pack_f16": ([_i] * 7 + [_p] * 6 + [_i, _p, _p, _p, _i, _p, _sz, _p], _i),
     "smk_linv_pack_f16": ([_i, _i, _p, _p, _p, _p, _p, _p], _i),
     "smk_predict_tc_f32": ([_i] * 6 + [_p] * 9 + [_i, _p, _p, _i, _p, _sz, _p, _i, _p, _p, _p], _i),

@@ -78,6 +78,7 @@ int trtri_split_tc(int, int, int, const float*, const float*, float*, float*, vo
 int linv_alpha(int, int, int, const float*, const float*, const float*, const float*, float*, int, float*, cudaStream_t);
 int linv_pack_f16(int, int, const float*, const float*, __half*, __half*, int*, cudaStream_t);
 size_t kxt_pack_workspace_bytes(int, int, int);
+int kxt_tc_timeline(long long*, int);
 int kxt_pack(int, int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
              const float*, int, __half*, __half*, float*, int, void*, size_t, cudaStream_t);
 int predict_tc(int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
@@ -197,6 +198,7 @@ int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* 
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream) {
   return linv_alpha(N, Np, S, linv_hi, linv_lo, y, mean, alpha, ld_alpha, tmp, ST(stream));
 }
+int smk_debug_kxt_tc_timeline(long long* out, int n) { return kxt_tc_timeline(out, n); }
 size_t smk_kxt_pack_workspace_bytes(int Np, int M, int S) { return kxt_pack_workspace_bytes(Np, M, S); }
 int smk_kxt_pack_f16(int impl, int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
                      const float* inv_ls, const float* amp2, const float* mean, const float* alpha, int Npad_alpha,

@@ -57,24 +57,31 @@ constexpr int MAXD = 32;           // padded dimension limit
 constexpr int MAXK = 96;           // J * Dp limit: one q stage = 128 x 96 halves x (hi, lo) = 48 KB
 constexpr int MAXS = 128;          // one sample per TMEM lane
 constexpr int THREADS = 16 * 32;
-constexpr int ALD = TN + 4;        // row length (floats) of the staged alpha tile: 528-byte stride -> conflict-free row reads
+constexpr int CW = 32;             // columns per epilogue chunk (one tcgen05.ld.x32)
+constexpr int ALD = CW + 4;        // row length (floats) of the staged alpha chunk: 144-byte stride -> conflict-free row reads
+constexpr int OLD = 144;           // bytes per row of the output staging: 64 B hi | 64 B lo | 16 B pad (conflict-free both ways)
+constexpr int GRP_OUT = 4 * 32 * OLD;            // output staging of one group (one [32 rows] block per warp)
+constexpr int GRP_BASE = 128 * 8;                // per-row global element offsets of the current item
 
 struct Args {
   int kind, N, Np, M, c_begin, Mc, D, Dp, S, J, K, Npad_alpha;
   int nitems;                      // ceil(candidates of the chunk / J)
   int mc_used;                     // candidates of this chunk (multiple of 128; rows beyond M are clamped copies)
-  const float *Xp, *Cp;            // scaled, zero-padded coordinates [Np][Dp], [..][Dp]
+  const float *Xp, *Cp;            // scaled, zero-padded coordinates: observations dimension-major [Dp][Np], candidates [..][Dp]
   const float *inv_ls, *amp2, *alpha;
   const unsigned* qmax;            // [2] float bits of max|X|, max|C|
   __half *khi, *klo;               // [S][Mc][Np]
   float* mu_partial;               // [NGRP][S][Mc]
+  long long* tl;                   // optional timeline (SMK_KXT_TIMELINE=1): [tile < 64][8] clock64() stamps of CTA 0
 };
+constexpr int TL_TILES = 64;
+__device__ long long g_timeline[TL_TILES * 8];
 
 __host__ __device__ inline int slots(int S, int Dp) { int j = 128 / S, k = MAXK / Dp; return j < k ? j : k; }
 
 __host__ __device__ inline size_t smem_bytes(int K, int S) {
   return (size_t)BSTAGES * 2 * TN * K * 2 + (size_t)2 * 128 * K * 2 + MAXK * 4 /*candidate rows*/ +
-         (size_t)NGRP * S * ALD * 4 /*alpha tiles*/ + 256 /*barriers*/ + 1024 /*align*/;
+         (size_t)NGRP * ((size_t)S * ALD * 4 /*alpha chunk*/ + GRP_OUT + GRP_BASE) + 256 /*barriers*/ + 1024 /*align*/;
 }
 
 // Operand tiles are K-major with the 64-byte swizzle (one candidate slot = 32 halves = one 64-byte row), stored as
@@ -117,8 +124,9 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
   unsigned char* sB = base;
   unsigned char* sW = sB + (size_t)BSTAGES * 2 * BH;
   float* cs = reinterpret_cast<float*>(sW + 2 * WH);             // [J][Dp] candidate rows of the current item
-  float* sAl = cs + MAXK;                                        // [NGRP][S][ALD] alpha tile of each epilogue group
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sAl + (size_t)NGRP * p.S * ALD);
+  unsigned char* sGrp = reinterpret_cast<unsigned char*>(cs + MAXK);   // per epilogue group: alpha chunk | output staging | row offsets
+  const size_t grp_bytes = (size_t)p.S * ALD * 4 + GRP_OUT + GRP_BASE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sGrp + NGRP * grp_bytes);
   uint64_t* b_full = bars;
   uint64_t* b_empty = b_full + BSTAGES;
   uint64_t* t_full = b_empty + BSTAGES;
@@ -186,10 +194,10 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
     const int r = tid;
     const uint64_t whi = desc_sw64(smem_u32(sW)), wlo = desc_sw64(smem_u32(sW + WH));
     const int ksteps = K / 16;
-    float4 xc[MAXD / 4], xn[MAXD / 4];
+    // Xp is stored dimension-major ([Dp][Np]): the 32 lanes of a warp read 128 contiguous bytes per dimension
+    float xc[MAXD], xn[MAXD];
 #pragma unroll
-    for (int k = 0; k < MAXD / 4; ++k)
-      xc[k] = (4 * k < Dp) ? __ldg(reinterpret_cast<const float4*>(p.Xp + (size_t)r * Dp) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < MAXD; ++d) xc[d] = __ldg(p.Xp + (size_t)d * p.Np + r);
     long t = 0;
     for (long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int c0 = p.c_begin + (int)item * p.J;     // first candidate of the item (rows of Cp beyond M are clamped copies)
@@ -200,11 +208,11 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
       for (int nb = 0; nb < nblocks; ++nb, ++t) {
         const int nbn = (nb + 1 == nblocks) ? 0 : nb + 1;
 #pragma unroll
-        for (int k = 0; k < MAXD / 4; ++k)
-          xn[k] = (4 * k < Dp) ? __ldg(reinterpret_cast<const float4*>(p.Xp + (size_t)(nbn * TN + r) * Dp) + k)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int d = 0; d < MAXD; ++d) xn[d] = __ldg(p.Xp + (size_t)d * p.Np + nbn * TN + r);
         const int st = (int)(t % BSTAGES);
         mbar_wait(&b_empty[st], (uint32_t)(((t / BSTAGES) & 1) ^ 1));
+        const bool stamp = p.tl && blockIdx.x == 0 && t < TL_TILES;
+        if (stamp && tid == 0) p.tl[t * 8 + 0] = clock64();
         unsigned char* bh = sB + (size_t)st * 2 * BH;
         unsigned char* bl = bh + BH;
         for (int j = 0; j < p.J; ++j) {
@@ -213,8 +221,8 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
             if (jb < CD) {
               const float4 c0v = *reinterpret_cast<const float4*>(&cs[j * Dp + 8 * jb]);
               const float4 c1v = *reinterpret_cast<const float4*>(&cs[j * Dp + 8 * jb + 4]);
-              const float4 x0 = xc[2 * jb], x1 = xc[2 * jb + 1];
-              const float2 xx[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
+              const float2 xx[4] = {make_float2(xc[8 * jb], xc[8 * jb + 1]), make_float2(xc[8 * jb + 2], xc[8 * jb + 3]),
+                                    make_float2(xc[8 * jb + 4], xc[8 * jb + 5]), make_float2(xc[8 * jb + 6], xc[8 * jb + 7])};
               const float2 cc[4] = {make_float2(-c0v.x, -c0v.y), make_float2(-c0v.z, -c0v.w), make_float2(-c1v.x, -c1v.y),
                                     make_float2(-c1v.z, -c1v.w)};
               __half2 hh[4], ll[4];
@@ -235,10 +243,13 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
         __syncwarp();
         if (lane == 0) mbar_arrive(&b_full[st]);
+        if (stamp && tid == 0) p.tl[t * 8 + 1] = clock64();
         if (warp == 3 && lane == 0) {                  // MMA issue for this tile
           const int b = (int)(t % TBUF);
+          if (stamp) p.tl[t * 8 + 2] = clock64();
           mbar_wait(&t_empty[b], (uint32_t)(((t / TBUF) & 1) ^ 1));
           mbar_wait(&b_full[st], (uint32_t)((t / BSTAGES) & 1));
+          if (stamp) p.tl[t * 8 + 3] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d = tmem_base + (uint32_t)b * TN;
           const uint32_t sb = smem_u32(bh);
@@ -251,10 +262,11 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
           }
           umma_commit(&b_empty[st]);
           umma_commit(&t_full[b]);
+          if (stamp) p.tl[t * 8 + 4] = clock64();
         }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < MAXD / 4; ++k) xc[k] = xn[k];
+        for (int d = 0; d < MAXD; ++d) xc[d] = xn[d];
       }
     }
   } else {
@@ -273,44 +285,50 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
     }
     const float2 scl2 = dup2(scl);
     const float2 a2s = dup2(a2 * ldexpf(1.f, kx_exp(a2)));
-    float* gal = sAl + (size_t)grp * p.S * ALD;      // this group's alpha tile [S][ALD]
+    unsigned char* gbase = sGrp + (size_t)grp * grp_bytes;
+    float* gal = reinterpret_cast<float*>(gbase);                                   // alpha chunk [S][ALD]
+    unsigned char* gout = gbase + (size_t)p.S * ALD * 4 + (size_t)q4 * 32 * OLD;    // this warp's output staging [32 rows][OLD]
+    long long* rowoff = reinterpret_cast<long long*>(gbase + (size_t)p.S * ALD * 4 + GRP_OUT);   // [128] element offsets, -1 = no row
     const float* al_row = gal + (size_t)(row_used ? s : 0) * ALD;
-    const int gt = tid - 128 - grp * 128;             // thread index inside the group (0..127)
+    const int gt = tid - 128 - grp * 128;             // thread index inside the group (0..127) == accumulator row L
     const int bar_id = 2 + grp;
     long t = 0;
     for (long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int crow = (int)item * p.J + j;           // candidate row inside the chunk
       const bool act = row_used && crow < p.mc_used;
-      const size_t orow = ((size_t)(act ? s : 0) * p.Mc + (act ? crow : 0)) * p.Np;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");            // the group is done with the previous item's offsets
+      rowoff[gt] = act ? (long long)(((size_t)s * p.Mc + crow) * p.Np) : -1;
       float2 v = make_float2(0.f, 0.f);
       for (int nb = 0; nb < nblocks; ++nb, ++t) {
         if ((int)(t % NGRP) != grp) continue;
         const int b = (int)(t % TBUF);
         const int n0 = nb * TN;
         const bool edge = n0 + TN > p.N;
-        // alpha_s[n0 .. n0+127] for all samples -> shared memory with coalesced 512-byte row reads (read per lane straight
-        // from global they were 30 sectors per request and 80 % of all stall samples: ncu r01, profiles/r01_kxt_tc_ncu.md)
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // previous tile's readers are done
-        for (int f = gt; f < p.S * (TN / 4); f += 128) {
-          const int rs = f >> 5, c4 = (f & 31) * 4, n = n0 + c4;
-          const float* src = p.alpha + (size_t)rs * p.Npad_alpha + n;
-          float4 a4;
-          if (n + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(src));
-          else a4 = make_float4(n < p.N ? src[0] : 0.f, n + 1 < p.N ? src[1] : 0.f, n + 2 < p.N ? src[2] : 0.f, 0.f);
-          *reinterpret_cast<float4*>(gal + (size_t)rs * ALD + c4) = a4;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const bool stamp = p.tl && blockIdx.x == 0 && t < TL_TILES && q4 == 0 && lane == 0;
+        if (stamp) p.tl[t * 8 + 5] = clock64();
         mbar_wait(&t_full[b], (uint32_t)((t / TBUF) & 1));
+        if (stamp) p.tl[t * 8 + 6] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)b * TN;
 #pragma unroll 1
-        for (int cq = 0; cq < TN; cq += 32) {
+        for (int cq = 0; cq < TN; cq += CW) {
           uint32_t r[32];
           tmem_ld32(t0 + cq, r);
+          // alpha_s[n0+cq .. +31] for all samples -> shared memory with coalesced 128-byte row reads
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // previous chunk's readers are done
+          for (int f = gt; f < p.S * (CW / 4); f += 128) {
+            const int rs = f >> 3, c4 = (f & 7) * 4, n = n0 + cq + c4;
+            const float* src = p.alpha + (size_t)rs * p.Npad_alpha + n;
+            float4 a4;
+            if (n + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(src));
+            else a4 = make_float4(n < p.N ? src[0] : 0.f, n + 1 < p.N ? src[1] : 0.f, n + 2 < p.N ? src[2] : 0.f, 0.f);
+            *reinterpret_cast<float4*>(gal + (size_t)rs * ALD + c4) = a4;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // (also publishes rowoff of a new item)
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (act) {
 #pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {             // 8 columns -> one 16-byte store of hi and of lo
+            for (int k8 = 0; k8 < 4; ++k8) {             // 8 columns -> 16 bytes of hi and of lo in this lane's staging row
               unsigned ph[4], pl[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
                   if (n >= p.N) kk.x = 0.f;
                   if (n + 1 >= p.N) kk.y = 0.f;
                 }
-                const float4 a4 = *reinterpret_cast<const float4*>(al_row + cq + (col & ~3));
+                const float4 a4 = *reinterpret_cast<const float4*>(al_row + (col & ~3));
                 const float2 ap = (col & 2) ? make_float2(a4.z, a4.w) : make_float2(a4.x, a4.y);
                 v = __ffma2_rn(kk, ap, v);
                 const float2 val = __fmul2_rn(kk, a2s);
@@ -334,15 +352,28 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
                 ph[i] = h2_bits(h2);
                 pl[i] = h2_bits(l2);
               }
-              const size_t o = orow + n0 + cq + 8 * k8;
-              *reinterpret_cast<uint4*>(p.khi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              *reinterpret_cast<uint4*>(p.klo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              *reinterpret_cast<uint4*>(gout + lane * OLD + k8 * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              *reinterpret_cast<uint4*>(gout + lane * OLD + 64 + k8 * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
           }
+          __syncwarp();
+          // coalesced write-out: each store instruction covers 4 rows x (64 B hi, 64 B lo); lane -> (row, half, 16-byte piece)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rho = 4 * i + (lane >> 3), seg = (lane >> 2) & 1, piece = lane & 3;
+            const long long off = rowoff[q4 * 32 + rho];
+            if (off >= 0) {
+              const uint4 dv = *reinterpret_cast<const uint4*>(gout + rho * OLD + seg * 64 + piece * 16);
+              __half* dst = (seg ? p.klo : p.khi) + off + n0 + cq + piece * 8;
+              *reinterpret_cast<uint4*>(dst) = dv;
+            }
+          }
+          __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[b]);
+        if (stamp) p.tl[t * 8 + 7] = clock64();
       }
       if (act) p.mu_partial[((size_t)grp * p.S + s) * p.Mc + crow] = v.x + v.y;
     }
@@ -364,7 +395,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(long n, const float* __rest
 }
 
 // out[r][d] = in[min(r, rows - 1)][d] * 2^(eq / 2) for d < D (zero for the padded dimensions; zero rows if zero_tail)
-__global__ void __launch_bounds__(256) kxt_prep_kernel(long rows_out, int rows, int D, int Dp, int zero_tail,
+__global__ void __launch_bounds__(256) kxt_prep_kernel(long rows_out, int rows, int D, int Dp, int zero_tail, int transpose,
                                                        const float* __restrict__ in, const unsigned* __restrict__ qmax,
                                                        float* __restrict__ out) {
   const float xmax = __uint_as_float(qmax[0]) + __uint_as_float(qmax[1]);
@@ -374,7 +405,8 @@ __global__ void __launch_bounds__(256) kxt_prep_kernel(long rows_out, int rows, 
     const int d = (int)(e % Dp);
     float x = 0.f;
     if (d < D && !(zero_tail && r >= rows)) x = in[(r < rows ? r : rows - 1) * D + d] * hs;
-    out[e] = x;
+    if (transpose) out[(long)d * rows_out + r] = x;      // dimension-major (observations: coalesced per-dimension reads)
+    else out[e] = x;
   }
 }
 
@@ -420,8 +452,8 @@ int kxt_tc_prepare(void* ws, int N, int Np, int M, int Mc, int D, int S, const f
   ktc::absmax_kernel<<<(unsigned)std::min<long>((nx + 255) / 256, 1024), 256, 0, st>>>(nx, X, pl.qmax);
   ktc::absmax_kernel<<<(unsigned)std::min<long>((nc + 255) / 256, 1024), 256, 0, st>>>(nc, Cc, pl.qmax + 1);
   const long rx = Np, rc = (long)kxt_cp_rows(M);
-  ktc::kxt_prep_kernel<<<(unsigned)std::min<long>((rx * Dp + 255) / 256, 4096), 256, 0, st>>>(rx, N, D, Dp, 1, X, pl.qmax, pl.Xp);
-  ktc::kxt_prep_kernel<<<(unsigned)std::min<long>((rc * Dp + 255) / 256, 4096), 256, 0, st>>>(rc, M, D, Dp, 0, Cc, pl.qmax, pl.Cp);
+  ktc::kxt_prep_kernel<<<(unsigned)std::min<long>((rx * Dp + 255) / 256, 4096), 256, 0, st>>>(rx, N, D, Dp, 1, 1, X, pl.qmax, pl.Xp);
+  ktc::kxt_prep_kernel<<<(unsigned)std::min<long>((rc * Dp + 255) / 256, 4096), 256, 0, st>>>(rc, M, D, Dp, 0, 0, Cc, pl.qmax, pl.Cp);
   count_launch(4);
   return check_launch("kxt_tc_prepare");
 }
@@ -442,6 +474,8 @@ int kxt_tc(void* ws, int kind, int N, int Np, int M, int c_begin, int Mc, int mc
   a.nitems = (mc_used + a.J - 1) / a.J;
   a.Xp = pl.Xp; a.Cp = pl.Cp; a.inv_ls = inv_ls; a.amp2 = amp2; a.alpha = alpha; a.qmax = pl.qmax;
   a.khi = khi; a.klo = klo; a.mu_partial = pl.mu_partial;
+  { const char* e = getenv("SMK_KXT_TIMELINE");
+    if (e && e[0] == '1') { void* sym = nullptr; cudaGetSymbolAddress(&sym, ktc::g_timeline); a.tl = reinterpret_cast<long long*>(sym); } }
   const size_t smem = ktc::smem_bytes(a.K, S);
   const int grid = (int)std::min<long>(a.nitems, num_sms());
   static bool attr = false;
@@ -452,6 +486,12 @@ int kxt_tc(void* ws, int kind, int N, int Np, int M, int c_begin, int Mc, int mc
   ktc::kxt_tc_kernel<<<grid, ktc::THREADS, smem, st>>>(a);
   count_launch();
   return check_launch("kxt_tc");
+}
+
+// debug: copies the timeline of the last launch made with SMK_KXT_TIMELINE=1 (64 tiles x 8 stamps) to the host
+int kxt_tc_timeline(long long* out, int n) {
+  if (n > ktc::TL_TILES * 8) n = ktc::TL_TILES * 8;
+  return cudaMemcpyFromSymbol(out, ktc::g_timeline, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
 }
 
 float* kxt_tc_mu_partial(void* ws, int Np, int Mc, int S, int M, int D) { return kxt_plan(ws, Np, Mc, S, M, D).mu_partial; }
