@@ -20,13 +20,14 @@
 // stores, 40 samples of state per thread and a transposing butterfly: 80 ms vs 64 ms for the SIMT kernel.)
 //
 // STATUS (round 1): numerically complete and parity-tested against the float64 oracle (tests/test_gpu_kernels.py::
-// test_kxt_generators_match_oracle), but NOT the production generator: with lane = (candidate, sample) every warp-level
-// 16-byte load of alpha and 16-byte store of the operand touches 32 different rows, i.e. ~8e9 separate L2 requests per
-// headline step against ~5e8 for the SIMT kernel's 128-byte-contiguous stores -- 144-148 ms vs 62-70 ms.  ncu (profiles/
-// r01_kxt_tc_ncu.md) shows nothing bandwidth-bound: the epilogue warps are starved for finished accumulators (358 M spins
-// on the accumulator barrier per launch) while tensor pipe, issue slots and L2 idle; staging alpha in shared memory, the
-// swizzled operand layout and restructured producers were each tried and are not the limiter.  Until the hand-off stall is
-// found predict_tc() uses the packed-float32 SIMT generator and this kernel is opt-in (SMK_KXT_IMPL=tc).
+// test_kxt_generators_match_oracle); 56-59 ms per headline step against 63-64 ms for the packed-float32 SIMT generator
+// (same box).  With lane = (candidate, sample) a naive epilogue issues 16-byte global accesses that are 32 separate sectors
+// per warp instruction; that version ran at 146 ms with every warp 8-10x slower than its instruction stream (clock64
+// timeline + ncu: profiles/r01_kxt_tc_ncu.md).  Hence the output chunk is transposed through shared memory before it is
+// stored (8 x 64-byte segments per store instruction), alpha is staged per 32-column chunk with coalesced reads, and the
+// observations are read dimension-major.  Opt-in (SMK_KXT_IMPL=tc) until it has been through a full verification round as
+// the default; predict_tc() uses the SIMT generator otherwise, and always for D > 32 or when the shared-memory budget of
+// this kernel does not fit the sample count.
 //
 // Roles in a CTA of 16 warps:  warps 0-3 producers (thread = observation row: q for the J candidate slots -> fp16 (hi, lo)
 // -> shared memory in the 64-byte-swizzled K-major layout, one [128 x 64 B] block per candidate slot; lane 0 of warp 3 also

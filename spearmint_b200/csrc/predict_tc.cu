@@ -1044,8 +1044,8 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   __half* ahi = reinterpret_cast<__half*>(partial + (size_t)npairs * S * Mc);   // alpha^T hi | lo  [S][Fp][Np]
   __half* alo = ahi + (size_t)S * Fp * Np;
   int* fexp = reinterpret_cast<int*>(alo + (size_t)S * Fp * Np);
-  // generator: the packed-float32 SIMT kernel is the production path (62-70 ms at the headline); the tensor-core
-  // generator of kxt_tc.cu is parity-complete but request-bound on its output path (148 ms) and opt-in: SMK_KXT_IMPL=tc
+  // generator: the packed-float32 SIMT kernel is the production path (62-65 ms at the headline); the tensor-core
+  // generator of kxt_tc.cu (56-59 ms, parity-complete) is opt-in until verified as the default: SMK_KXT_IMPL=tc
   static int gen_env = -1;
   if (gen_env < 0) { const char* e = getenv("SMK_KXT_IMPL"); gen_env = (e && !strcmp(e, "tc")) ? 1 : 0; }
   const bool gen_tc = gen_env == 1 && kxt_tc_supported(D, S) && nbuf == 1;
