@@ -365,7 +365,6 @@ def next_wall_ms(args):
     configuration (D=8, N=512, 10k candidates, 10 hyper-samples, reference defaults burnin=100, grid_subset=20); the CPU
     figure (same host logic on the oracle numerics = a port of the reference's next()) only with --next-cpu: it takes
     ~20 s per call."""
-    import tempfile
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import next_bench
     D, N, M, S = WORKLOADS["c2"]

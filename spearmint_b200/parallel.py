@@ -8,8 +8,6 @@ candidate grid; the message is M floats (400 KB at M=100k) -- latency-sized, so 
 compute stream right behind the last EI sweep.  The sample->rank map and the summation order inside
 a rank are fixed, so results are reproducible for a given world size.
 """
-import numpy as np
-import torch
 import torch.distributed as dist
 
 

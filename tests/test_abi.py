@@ -1,6 +1,5 @@
 """CPU: the C-ABI shared library builds, loads, and exports every symbol include/*.h declares
 (no compute calls -- there is no GPU in the build container)."""
-import ctypes
 import os
 import re
 

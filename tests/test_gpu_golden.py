@@ -9,7 +9,7 @@ The float64 build of the same kernels must agree to 1e-7 relative (logic check, 
 import numpy as np
 import pytest
 
-from tests.helpers import OPT_CASES, PSEC_CASES, hypers, load, sets
+from tests.helpers import OPT_CASES, hypers, load, sets
 
 pytestmark = pytest.mark.gpu
 
