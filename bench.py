@@ -146,7 +146,8 @@ def cpu_port_sample(D, N, M, S, budget_cands=None, threads=None):
     from oracle import gp_oracle as O
     import scipy.linalg as spla
     comp, cand, vals, hs = synth(D, N, M, S)
-    if budget_cands is None:   # ~10-30 s of CPU work
+    budget_cands_auto = budget_cands is None
+    if budget_cands is None:   # first guess; grown below if the host is fast
         budget_cands = int(max(500, min(M, 2.0e11 / (float(N) * N + 60.0 * N * D))))
     Mc = min(M, budget_cands)
     h = hs[0]
@@ -156,13 +157,19 @@ def cpu_port_sample(D, N, M, S, budget_cands=None, threads=None):
     L = spla.cholesky(K, lower=True)
     alpha = spla.cho_solve((L, True), vals - mean)
     t_fixed = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    Kx = O.cov(KIND, amp2, ls, comp, cand[:Mc])
-    beta = spla.solve_triangular(L, Kx, lower=True)
-    m = np.dot(Kx.T, alpha) + mean
-    v = amp2 * (1 + 1e-6) - np.sum(beta ** 2, axis=0)
-    ei = O._ei_from_moments(np.min(vals), m, np.sqrt(v))
-    t_cand = time.perf_counter() - t0
+    def candidates_part(mc):
+        t0 = time.perf_counter()
+        Kx = O.cov(KIND, amp2, ls, comp, cand[:mc])
+        beta = spla.solve_triangular(L, Kx, lower=True)
+        m = np.dot(Kx.T, alpha) + mean
+        v = amp2 * (1 + 1e-6) - np.sum(beta ** 2, axis=0)
+        e = O._ei_from_moments(np.min(vals), m, np.sqrt(v))
+        return time.perf_counter() - t0, e
+
+    t_cand, ei = candidates_part(Mc)
+    if budget_cands_auto and t_cand < 5.0 and Mc < M:      # many-core hosts: grow the sample to ~10 s of CPU work
+        Mc = int(min(M, 50000, max(Mc, Mc * 10.0 / max(t_cand, 1e-3))))   # (<= 1.6 GB per N x Mc float64 temporary)
+        t_cand, ei = candidates_part(Mc)
     t_full = S * (t_fixed + t_cand * (float(M) / Mc))
     return dict(value=M / t_full, t_full_s=t_full, t_fixed_s=t_fixed, t_cand_s=t_cand, Mc=Mc,
                 sample="1 hyper-sample, N=%d, %d of %d candidates; extrapolated linearly to S=%d, M=%d "
