@@ -222,12 +222,25 @@ class GPEIEngine(object):
         return self._ws
 
     def max_samples_per_chunk(self, Npad, ldm, F=1):
-        """How many hyper-samples fit at once (factor + winv + alpha + mu/var/ei) in ~70% of free HBM."""
+        """How many hyper-samples fit at once in ~70% of free HBM: factor + winv + alpha + mu/var/ei per sample, plus --
+        on the tensor-core path -- the explicit inverse (tf32 pair, fp16 pair, the transposed pair of the inversion
+        workspace: 20 B per element of Np^2) and the cross-covariance chunk (4 B per (candidate, observation) and
+        sample, capped by the library's 20 GB chunk budget)."""
         free, _ = torch.cuda.mem_get_info(self.device)
         free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        budget = 0.7 * free
         per = self.esize * (Npad * Npad + Npad * self.NB + F * Npad + (F + 3) * ldm)
+        if self.predict_impl == "tc" and self.dtype == torch.float32:
+            Np = _ceil(Npad, 256)
+            per += 20 * Np * Np
+            per_kxt = 4.0 * ldm * Np + 4.0 * (Np // 512 + 1) * ldm      # operand chunk + row-group-pair partials
+            cap = float(21 << 30)
+            s1 = budget / (per + per_kxt)
+            if s1 * per_kxt <= cap:
+                return max(1, int(s1))
+            return max(1, int((budget - cap) // per))
         fixed = _lib.lib().smk_predict_workspace_bytes(self.esize, Npad)
-        return max(1, int((0.7 * free - fixed) // per))
+        return max(1, int((budget - fixed) // per))
 
     # ------------------------------------------------------------------ building blocks
     def hypers(self, hyper_samples, kind):
