@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- EI candidates/sec of the GP-EI chooser hot path (BASELINE.json metric).
+"""bench.py -- EI candidates/sec of the GP-EI chooser hot path, and chooser.next() wall-ms (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
@@ -9,29 +9,43 @@ generator -> tcgen05 predict GEMM (3xFP16 scaled split) -> EI sweep (-> all-redu
 N > 1) -> argmax.
 
   value : M / step-time with X, candidates, values and hyper-samples already resident in HBM.
-  e2e   : the same metric through the host-facing call (numpy in, (M,S) EI matrix out), host<->device copies
-          inside the timed region.
+  e2e   : the same metric through the reference-facing plugin call (``chooser.ei_over_hypers(comp, pend, cand, vals)``:
+          host numpy in, (M, S) float64 EI matrix out, then the host argmax of the mean), host<->device copies inside
+          the timed region, --steps iterations.
   roofline     : the dominant kernel (tc::predict_tc_kernel, the N^2*M triangular-solve term as a GEMM against the
-                 explicit inverse), algorithmic flops / its CUDA-event time vs the measured dense bf16 tensor peak
-                 (MEASURED_PEAKS.json); traffic = DRAM bytes per launch from the ncu capture in profiles/.
-  cpu_baseline : the oracle port (numpy/scipy, the reference's own operation sequence) timed on this box's
-                 host cores on a bounded sample of the same workload and extrapolated linearly (the reference
-                 loop is exactly linear in S and in M for fixed N).
-  --impl reference : that CPU implementation as its own arm (rank 0 only).
+                 explicit inverse): algorithmic flops / its CUDA-event time vs the measured dense bf16 tensor peak
+                 (MEASURED_PEAKS.json); traffic = DRAM bytes per launch read from the committed ncu summary
+                 profiles/r02_predict_tc_traffic.json (bench.py never runs under a profiler).
+  cpu_baseline : the oracle port (oracle.gp_oracle.compute_ei: the reference's own numpy/scipy operation sequence,
+                 GPEIOptChooser.py:527-556) timed on this box's host cores -- BLAS threads pinned to all of them, the same
+                 at every --gpus N -- on a bounded sample and extrapolated linearly (the reference loop is exactly
+                 linear in S and, for fixed N, affine in M).  Its EI values are compared with the GPU's
+                 (``parity``: max |dEI| / max EI over the sample, argmax equality).
+  next  : chooser.next() wall-ms through the plugin API at the SAME workload, steady state (no burn-in), with the phase
+          split (MCMC / grid pass 1 / L-BFGS refinement / grid pass 2) and the CPU port's time as counts x unit times.
+  --impl reference : the CPU implementation as its own arm (rank 0 only).
 
 Multi-GPU: hyper-samples are sharded round-robin over ranks (total work fixed -> "scaling": "strong"); the
 only exchange is one NCCL all-reduce of M floats.
 """
-import argparse
-import ctypes
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# BLAS / OpenMP threads of the CPU arm: all host cores, decided HERE, before numpy loads its BLAS.  torchrun exports
+# OMP_NUM_THREADS=1 to every rank; without this the CPU baseline would be ~2.4x slower under --gpus N > 1 than at N = 1.
+_CORES = os.cpu_count() or 1
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(_CORES)
+
+import argparse   # noqa: E402
+import ctypes     # noqa: E402
+import json       # noqa: E402
+import subprocess  # noqa: E402
+import tempfile   # noqa: E402
+import threading  # noqa: E402
+import time       # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -41,9 +55,11 @@ WORKLOADS = {
     "headline": (32, 4096, 100000, 40),   # "EI candidates/sec (N=4096 obs, 100k cands, 40 hypers)"
     "c2": (8, 512, 10000, 10),
     "c3": (20, 2048, 50000, 20),
+    "c4": (8, 1024, 20000, 10),           # GPEIperSecChooser dual GP (objective + cost); D, S: SURVEY 8 defaults
     "c5": (32, 8192, 100000, 40),
     "tiny": (4, 96, 2000, 4),
 }
+PER_SECOND = ("c4",)                       # workloads that run the EI-per-second path (PSEC:437-548)
 KIND = "Matern52"
 
 
@@ -60,23 +76,30 @@ def synth(D, N, M, S):
     return comp, cand, vals, hs
 
 
+def synth_time(D, comp, S):
+    """Duration GP of the per-second workloads: durations = 1 + x_0, its own hyper-samples."""
+    durs = np.log(1.0 + comp[:, 0])
+    rs = np.random.RandomState(5)
+    ths = [(float(np.mean(durs)) + 0.05 * rs.randn(), 1e-3, float(np.exp(0.25 * rs.randn())), rs.uniform(0.3, 2.0, D))
+           for _ in range(S)]
+    return durs, ths
+
+
 def flops_per_pair(N, D):
     """algorithmic flops per (candidate, hyper-sample) pair."""
     return float(N) * N + 2.0 * N * D + 4.0 * N + 25.0 * N + 40.0
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE predict-GEMM launch over a full 32768-candidate chunk
-# of the headline workload on one GPU, from the `ncu --set full` capture summarised in profiles/ (bench.py never runs
-# under a profiler).  A step has 3 such launches + a 1696-candidate tail; the per-launch average is reported.
-NCU_TRAFFIC = {"headline": {"bytes_per_full_chunk_launch": 37.82e9, "chunk_cands": 32768,
-                            "source": "profiles/r01_predict_tc_final_ncu.md"}}
-
-
-def ncu_traffic(workload, impl, world, M, launches_per_step):
-    t = NCU_TRAFFIC.get(workload)
-    if t is None or impl != "tc" or world != 1:
-        return None
-    return t["bytes_per_full_chunk_launch"] * (float(M) / t["chunk_cands"]) / max(1, launches_per_step)
+def ncu_traffic(workload, impl, world, launches_per_step):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary (which names its capture commit)."""
+    p = os.path.join(ROOT, "profiles", "r02_predict_tc_traffic.json")
+    if impl != "tc" or world != 1 or not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    w = d.get("workloads", {}).get(workload)
+    if not w:
+        return None, None
+    return float(w["dram_bytes_per_step"]) / max(1, launches_per_step), "profiles/r02_predict_tc_traffic.json @ %s" % d.get("commit")
 
 
 def peaks():
@@ -120,12 +143,13 @@ class ClockSampler(object):
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for k, n in enumerate(names):
                     if r[5 + k].lower().startswith("active"):
                         reasons.add(n)
@@ -134,57 +158,70 @@ class ClockSampler(object):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_median": float(np.median(pw)) if pw else None}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_port_sample(D, N, M, S, budget_cands=None, threads=None):
-    """Times the oracle port on host cores on a bounded sample and extrapolates to the full (M, S) pass.
+def blas_threads():
+    """Pins every BLAS / OpenMP pool numpy and scipy loaded to all host cores; returns what is in effect."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=_CORES)
+        info = threadpoolctl.threadpool_info()
+        return max([int(i.get("num_threads", 1)) for i in info] or [1])
+    except Exception:
+        return _CORES
 
-    The reference loop is linear in S (OPT:333-340) and, for fixed N, in M (every stage after the Cholesky is
-    per-candidate), so   t_full = S * (t_fixed + t_cand * M / M_cpu)."""
+
+def cpu_port_sample(workload, D, N, M, S, budget_cands=None):
+    """Times the oracle port (O.compute_ei / O.compute_ei_per_s: the reference's operation sequence) on host cores on a
+    bounded sample and extrapolates to the full (M, S) pass.
+
+    compute_ei is affine in the number of candidates for fixed N (K build + Cholesky + alpha once, then per-candidate
+    work) and ei_over_hypers is a plain loop over S (OPT:333-340), so two timings of ONE hyper-sample at m0 and Mc
+    candidates give   t_full = S * (t_fixed + t_cand_per * M)."""
     from oracle import gp_oracle as O
-    import scipy.linalg as spla
+    threads = blas_threads()
     comp, cand, vals, hs = synth(D, N, M, S)
-    budget_cands_auto = budget_cands is None
-    if budget_cands is None:   # first guess; grown below if the host is fast
-        budget_cands = int(max(500, min(M, 2.0e11 / (float(N) * N + 60.0 * N * D))))
-    Mc = min(M, budget_cands)
-    h = hs[0]
-    t0 = time.perf_counter()
-    mean, noise, amp2, ls = h
-    K = O.cov(KIND, amp2, ls, comp) + noise * np.eye(N)
-    L = spla.cholesky(K, lower=True)
-    alpha = spla.cho_solve((L, True), vals - mean)
-    t_fixed = time.perf_counter() - t0
-    def candidates_part(mc):
+    pend = np.zeros((0, D))
+    per_s = workload in PER_SECOND
+    if per_s:
+        durs, ths = synth_time(D, comp, S)
+
+    def one(mc):
         t0 = time.perf_counter()
-        Kx = O.cov(KIND, amp2, ls, comp, cand[:mc])
-        beta = spla.solve_triangular(L, Kx, lower=True)
-        m = np.dot(Kx.T, alpha) + mean
-        v = amp2 * (1 + 1e-6) - np.sum(beta ** 2, axis=0)
-        e = O._ei_from_moments(np.min(vals), m, np.sqrt(v))
+        if per_s:
+            e = O.compute_ei_per_s(KIND, hs[0], ths[0], comp, pend, cand[:mc], vals, durs)
+        else:
+            e = O.compute_ei(KIND, hs[0], comp, pend, cand[:mc], vals)
         return time.perf_counter() - t0, e
 
-    t_cand, ei = candidates_part(Mc)
-    if budget_cands_auto and t_cand < 5.0 and Mc < M:      # many-core hosts: grow the sample to ~10 s of CPU work
-        Mc = int(min(M, 50000, max(Mc, Mc * 10.0 / max(t_cand, 1e-3))))   # (<= 1.6 GB per N x Mc float64 temporary)
-        t_cand, ei = candidates_part(Mc)
-    t_full = S * (t_fixed + t_cand * (float(M) / Mc))
-    return dict(value=M / t_full, t_full_s=t_full, t_fixed_s=t_fixed, t_cand_s=t_cand, Mc=Mc,
-                sample="1 hyper-sample, N=%d, %d of %d candidates; extrapolated linearly to S=%d, M=%d "
-                       "(t_fixed=%.2fs K+chol+alpha, t_cand=%.2fs)" % (N, Mc, M, S, M, t_fixed, t_cand),
-                checksum=float(np.sum(ei)))
+    m0 = min(M, 16)
+    one(m0)                                                   # warm-up (BLAS thread pools, page faults)
+    t_small, _ = one(m0)
+    auto = budget_cands is None
+    Mc = int(min(M, budget_cands if not auto else max(500, 2.0e11 / (float(N) * N + 60.0 * N * D))))
+    t_big, ei = one(Mc)
+    if auto and t_big < 8.0 and Mc < M:                       # many-core hosts: grow the sample to ~15 s of CPU work
+        Mc = int(min(M, 60000, max(Mc, Mc * 15.0 / max(t_big - t_small, 1e-3))))   # (<= 2 GB per N x Mc float64 temporary)
+        t_big, ei = one(Mc)
+    per_cand = max(t_big - t_small, 1e-9) / max(Mc - m0, 1)
+    t_fixed = max(t_small - per_cand * m0, 0.0)
+    t_full = S * (t_fixed + per_cand * M)
+    return dict(value=M / t_full, t_full_s=t_full, t_fixed_s=t_fixed, t_cand_s=per_cand * Mc, Mc=Mc, ei=ei, threads=threads,
+                sample="oracle.gp_oracle.%s on 1 of %d hyper-samples, N=%d, %d and %d of %d candidates (%.1f s of CPU "
+                       "work, %d BLAS threads); affine fit extrapolated to S=%d, M=%d (t_fixed=%.2fs K+chol+alpha, "
+                       "%.3f ms per candidate)" % ("compute_ei_per_s" if per_s else "compute_ei", S, N, m0, Mc, M,
+                                                   2 * t_small + t_big, threads, S, M, t_fixed, 1e3 * per_cand))
 
 
 def run_reference_arm(args, D, N, M, S):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
     vals = []
     for it in range(args.warmup + args.steps):
-        r = cpu_port_sample(D, N, M, S, budget_cands=args.cpu_cands)
+        r = cpu_port_sample(args.workload, D, N, M, S, budget_cands=args.cpu_cands)
         if it >= args.warmup:
             vals.append(r)
     t = float(np.mean([r["t_full_s"] for r in vals]))
@@ -195,7 +232,7 @@ def run_reference_arm(args, D, N, M, S):
            "config": {"workload": "%s D=%d N=%d M=%d S=%d %s" % (args.workload, D, N, M, S, KIND),
                       "note": "oracle port of the reference numpy/scipy path (the py2 reference cannot travel); "
                               "each step times a bounded sample and extrapolates linearly"},
-           "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": cores, "kind": "port",
+           "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": vals[-1]["threads"], "kind": "port",
                             "sample": vals[-1]["sample"]},
            "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -207,7 +244,7 @@ def run_b200_arm(args, D, N, M, S):
     import torch
     import torch.distributed as dist
     from spearmint_b200 import _lib, parallel
-    from spearmint_b200.engine import GPEIEngine
+    from spearmint_b200.backend import DeviceBackend
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,10 +255,15 @@ def run_b200_arm(args, D, N, M, S):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
-    eng = GPEIEngine(device="cuda:%d" % local, dtype=torch.float32)
+    backend = DeviceBackend(device="cuda:%d" % local)
+    eng = backend.eng32
     comp, cand, vals, hs = synth(D, N, M, S)
+    pend = np.zeros((0, D))
+    per_s = args.workload in PER_SECOND
+    durs, ths = synth_time(D, comp, S) if per_s else (None, None)
     mine = parallel.shard(S, rank, world)
     hs_local = [hs[s] for s in mine]
+    ths_local = [ths[s] for s in mine] if per_s else None
     Sl = len(hs_local)
 
     # ---- resident inputs for the `value` leg
@@ -232,24 +274,28 @@ def run_b200_arm(args, D, N, M, S):
     def step_resident():
         if Sl:
             _, ei_sum, _ = eng.ei_over_hypers_device(KIND, hs_local, None, None, None, None, want_matrix=False,
-                                                     inputs_on_device=res)
+                                                     inputs_on_device=res, time_hyper_samples=ths_local, durs_log=durs)
         else:
             ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
         parallel.allreduce_sum_(ei_sum)
         idx, _ = eng.topk(ei_sum, M, 1)
         return idx
 
+    # ---- e2e leg: the plugin call.  GPEIOptChooserB200.ei_over_hypers is the drop-in for OPT:331-341; the per-second
+    # plugin's method reproduces the reference's column-0-only early return (PSEC:302), so that workload goes through the
+    # backend calls the plugin makes (grid_state + ei_matrix) with every column.
+    from spearmint_b200.chooser import GPEIOptChooserB200 as plugin
+    ch = plugin.init(tempfile.mkdtemp(), "mcmc_iters=%d,burnin=0,noiseless=1" % S)
+    ch._backend = backend
+    ch.D, ch.hyper_samples = D, list(hs)
+
     def step_e2e():
-        # host numpy in -> H2D -> path -> D2H of this rank's (M, S_local) EI columns + all-reduced argmax
-        if Sl:
-            ei, ei_sum, _ = eng.ei_over_hypers_device(KIND, hs_local, comp, None, cand, vals, want_matrix=True)
-            host = ei[:, :M].t().contiguous().cpu()
+        if per_s:
+            st = backend.grid_state(KIND, hs, comp, pend, vals, None, ths, durs)
+            ei = backend.ei_matrix(st, cand)
         else:
-            ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
-            host = None
-        parallel.allreduce_sum_(ei_sum)
-        idx, _ = eng.topk(ei_sum, M, 1)
-        return host, int(idx.cpu()[0])
+            ei = ch.ei_over_hypers(comp, pend, cand, vals)        # (M, S) float64 on the host
+        return ei, int(np.argmax(ei.mean(axis=1)))
 
     def barrier():
         if world > 1:
@@ -263,7 +309,7 @@ def run_b200_arm(args, D, N, M, S):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.timers = {} if with_timers else None
         L.smk_timing_enable(1 if with_timers else 0)
-        l0 = _lib.lib().smk_launch_count()
+        l0 = L.smk_launch_count()
         w0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
@@ -272,11 +318,9 @@ def run_b200_arm(args, D, N, M, S):
         barrier()
         wall = time.perf_counter() - w0
         ms = e0.elapsed_time(e1)
-        launches = _lib.lib().smk_launch_count() - l0
+        launches = L.smk_launch_count() - l0
         stages = eng.stage_ms()
         eng.timers = None
-        if not with_timers:
-            pass
         t = torch.tensor([ms, wall * 1e3, float(launches)], dtype=torch.float64, device=eng.device)
         if world > 1:
             tmax = t.clone()
@@ -304,13 +348,14 @@ def run_b200_arm(args, D, N, M, S):
         c2 = ctypes.c_int(0)
         span[nm] = (L.smk_timing_ms(nm.encode(), ctypes.byref(c2)), c2.value)
 
-    # ---- e2e leg (host buffers through the public call), device-event timed around host work too
+    # ---- e2e leg (host buffers through the plugin call); wall-clock over host + device work, max over ranks
     step_e2e()
-    _, wall_ms, _, _, (host, best_idx) = timed(step_e2e, max(1, min(args.steps, 3)))
-    e2e_ms = wall_ms / max(1, min(args.steps, 3))
+    _, wall_ms, _, _, (ei_host, best_idx) = timed(step_e2e, args.steps)
+    e2e_ms = wall_ms / args.steps
     esz = 4
-    h2d = esz * (comp.size + cand.size + vals.size) + esz * Sl * (D + 3)
-    d2h = 8 * M * Sl + 4       # the (M, S_local) EI matrix is float64 (tail values), + the argmax index
+    n_gp = 2 if per_s else 1
+    h2d = esz * (comp.size + cand.size + n_gp * vals.size) + esz * n_gp * Sl * (D + 3)
+    d2h = 8 * ldm * (S if world > 1 else Sl)      # the EI matrix is float64 (tail values)
 
     if rank == 0:
         pk = peaks()
@@ -328,11 +373,12 @@ def run_b200_arm(args, D, N, M, S):
         for nm in ("kxt_kernel", "trtri_kernel", "linv_pack_f16"):
             if span[nm][1]:
                 other[nm + "_ms_per_step"] = span[nm][0] / args.steps
+        traffic, traffic_src = ncu_traffic(args.workload, impl, world, n_launch_step)
         roof = {"kernel": "smk::tc::predict_tc_kernel (tcgen05.mma kind::f16, 3xFP16 scaled split, fp32 accumulate)" if impl == "tc"
                 else "smk::predict_kernel<float> (SIMT FMA)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": (achieved / pk["tensor_sustained"]) if achieved else None,
-                "traffic": ncu_traffic(args.workload, impl, world, M, n_launch_step) if Sl == 40 else None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": alg / n_launch_step, "launches_per_step": n_launch_step,
                 "kernel_ms_per_launch": kms_step / n_launch_step, "kernel_ms_per_step": kms_step,
@@ -341,7 +387,6 @@ def run_b200_arm(args, D, N, M, S):
                         "bf16 peak is this formulation's ceiling"
                         if impl == "tc" else "float32 SIMT FMA path (B200 fp32 vector peak ~74 TFLOP/s)",
                 "stage_ms_per_step": dict({k: v / args.steps for k, v in stages.items()}, **other)}
-        cpu = cpu_port_sample(D, N, M, S, budget_cands=args.cpu_cands) if world == 1 and not args.no_cpu else None
         out = {"metric": "EI candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -351,39 +396,71 @@ def run_b200_arm(args, D, N, M, S):
                           "l2": "working set (factors %.1f GB per rank) >> 126 MB L2, no flush needed"
                                 % (Sl * (((N + 127) // 128) * 128) ** 2 * 4 / 1e9),
                           "pairs_per_sec": value * S, "argmax": int(idx.cpu()[0]), "argmax_e2e": best_idx},
-               "e2e": {"value": M / (e2e_ms * 1e-3), "unit": "candidates/s", "ms_per_step": e2e_ms,
+               "e2e": {"value": M / (e2e_ms * 1e-3), "unit": "candidates/s", "ms_per_step": e2e_ms, "steps": args.steps,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "api": "GPEIEngine.ei_over_hypers_device(host numpy) -> (M,S_local) EI matrix on host"},
+                       "api": ("backend.grid_state + backend.ei_matrix (the calls GPEIperSecChooserB200 makes)" if per_s else
+                               "GPEIOptChooserB200.ei_over_hypers(comp, pend, cand, vals)") +
+                              " -> (M,S) float64 EI matrix on the host, host argmax of the mean"},
                "gpu_launches": launches, "clocks": clocks, "roofline": roof}
-        if cpu is not None:
-            out["cpu_baseline"] = {"value": cpu["value"], "unit": "candidates/s", "cores": os.cpu_count(),
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_port_sample(args.workload, D, N, M, S, budget_cands=args.cpu_cands)
+            out["cpu_baseline"] = {"value": cpu["value"], "unit": "candidates/s", "cores": cpu["threads"],
                                    "kind": "port", "sample": cpu["sample"]}
-        if world == 1 and not args.no_next:
-            out["next"] = next_wall_ms(args)
+            ref, got = cpu["ei"], ei_host[:cpu["Mc"], 0]        # sample 0 lives on rank 0 (column 0 of the matrix)
+            out["parity"] = {"vs": "cpu_baseline sample (hyper-sample 0, first %d candidates)" % cpu["Mc"],
+                             "parity_max_rel": float(np.abs(got - ref).max() / ref.max()),
+                             "argmax_match": bool(int(np.argmax(got)) == int(np.argmax(ref))),
+                             "tolerance": 5e-3}
+            cpu.pop("ei")
+        if world == 1 and not args.no_next and not per_s:
+            out["next"] = next_wall_ms(args, D, N, M, S, backend)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def next_wall_ms(args):
-    """Second half of BASELINE.json's metric: chooser.next() wall-ms through the plugin API (MCMC chain with the GPU
-    float64 log-likelihood -> grid pass -> L-BFGS refinement with cached factors -> grid pass).  Measured at the `c2`
-    configuration (D=8, N=512, 10k candidates, 10 hyper-samples, reference defaults burnin=100, grid_subset=20); the CPU
-    figure (same host logic on the oracle numerics = a port of the reference's next()) only with --next-cpu: it takes
-    ~20 s per call."""
+def next_wall_ms(args, D, N, M, S, backend):
+    """Second half of BASELINE.json's metric: chooser.next() wall-ms through the plugin API at the benched workload
+    (MCMC chain with the GPU float64 log-likelihood -> grid pass -> L-BFGS refinement with cached factors -> grid pass),
+    steady state: burnin=0 stands for "second call" (the first call of a real run adds `burnin`=100 more sample_hypers).
+
+    The CPU port of the same call is reported as counts x unit times (the full reference next() at the
+    headline size is multi-hour): log-likelihood evaluations x one O.gp_logprob, refinement evaluations x S x one
+    O.grad_optimize_ei, two grid passes from the cpu_baseline fit.  --next-cpu runs the CPU port for real (small
+    workloads only)."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import next_bench
-    D, N, M, S = WORKLOADS["c2"]
-    calls = next_bench.run("gpu", D, N, M, S, burnin=100, calls=3, grid_subset=20)
-    out = {"workload": "c2 D=%d N=%d M=%d S=%d burnin=100 grid_subset=20" % (D, N, M, S),
-           "ms_first_call_with_burnin": calls[0]["ms"], "ms_steady": float(np.mean([c["ms"] for c in calls[1:]])),
-           "unit": "ms", "refine_evals": calls[-1]["refine_evals"]}
+    calls = next_bench.run("gpu", D, N, M, S, burnin=0, calls=args.next_calls, grid_subset=20, backend=backend)
+    last = calls[-1]
+    out = {"workload": "%s D=%d N=%d M=%d S=%d burnin=0 (steady state) grid_subset=20" % (args.workload, D, N, M, S),
+           "ms": float(np.mean([c["ms"] for c in calls])), "unit": "ms", "calls": len(calls),
+           "phase_ms": last["phase_ms"], "loglik_evals": last["loglik_evals"], "loglik_batches": last["loglik_batches"],
+           "refine_evals": last["refine_evals"]}
+    if not args.no_cpu:
+        from oracle import gp_oracle as O
+        blas_threads()
+        comp, cand, vals, hs = synth(D, N, M, S)
+        pend = np.zeros((0, D))
+        h = hs[0]
+        O.gp_logprob(KIND, h[0], h[1], h[2], h[3], comp, vals)
+        t0 = time.perf_counter()
+        O.gp_logprob(KIND, h[0], h[1], h[2], h[3], comp, vals)
+        t_ll = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.grad_optimize_ei(KIND, h, cand[:1], comp, pend, vals)
+        t_g = time.perf_counter() - t0
+        grid = cpu_port_sample(args.workload, D, N, M, S, budget_cands=min(M, 2000))
+        est = last["loglik_evals"] * t_ll + last["refine_evals"] * S * t_g + 2.0 * grid["t_full_s"]
+        out["cpu_port_estimate"] = {
+            "ms": 1e3 * est, "kind": "counts x unit times (extrapolation, not a timed run)",
+            "loglik_unit_s": t_ll, "refine_eval_unit_s_per_sample": t_g, "grid_pass_s": grid["t_full_s"],
+            "formula": "loglik_evals*t_loglik + refine_evals*S*t_grad + 2*t_grid_pass", "cores": _CORES}
+        out["speedup_vs_cpu_port_estimate"] = (1e3 * est) / out["ms"]
     if args.next_cpu:
-        cpu = next_bench.run("cpu", D, N, M, S, burnin=100, calls=2, grid_subset=20)
-        out["cpu_port_ms_steady"] = cpu[-1]["ms"]
-        out["cpu_port_ms_first_call"] = cpu[0]["ms"]
-        out["cpu_cores"] = os.cpu_count()
+        cpu = next_bench.run("cpu", D, N, M, S, burnin=0, calls=1, grid_subset=20)
+        out["cpu_port_ms_timed"] = cpu[-1]["ms"]
+        out["cpu_cores"] = _CORES
     return out
 
 
@@ -398,7 +475,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--samples", type=int, default=None, help="override S (experiments only)")
     ap.add_argument("--no-next", action="store_true", help="skip the chooser.next() wall-ms leg")
-    ap.add_argument("--next-cpu", action="store_true", help="also time the CPU port of next() (slow)")
+    ap.add_argument("--next-calls", type=int, default=1, help="timed next() calls")
+    ap.add_argument("--next-cpu", action="store_true", help="also run the CPU port of next() for real (slow)")
     args = ap.parse_args()
     D, N, M, S = WORKLOADS[args.workload]
     if args.samples:

@@ -93,6 +93,15 @@ int smk_loglik_set_rhs_f64(int N, int Npad, int S, const double* y, const double
 int smk_loglik_finish_f32(int N, int Npad, int S, const float* L, float* sum_log_diag, float* quad, void* stream);
 int smk_loglik_finish_f64(int N, int Npad, int S, const double* L, double* sum_log_diag, double* quad, void* stream);
 
+/* ---- (3c) float64 Cholesky of the log-likelihood path (the spla.cholesky inside every slice-sampler logprob,
+ * OPT:637, 659, 690): NB = 128 right-looking with one step of look-ahead on two internal streams, diagonal blocks on one
+ * SM (warp-synchronous), panel and trailing update on the fp64 tensor path (mma.sync.m8n8k4.f64).  A: [S][Npad][Npad]
+ * (lower triangle in/out, Npad % 128 == 0), info[S] as in (2).  use_graph != 0: the launch sequence is captured into a
+ * CUDA graph per (A, workspace, info, Npad, S) on first use and replayed afterwards.  Only L is produced.          */
+size_t smk_potrf_loglik_workspace_bytes(int Npad, int S);
+int smk_potrf_loglik_f64(int Npad, int S, double* A, void* workspace, size_t workspace_bytes, int* info, int use_graph,
+                         void* stream);
+
 /* ---- (4) fused predict: cross-covariance tiles generated on the fly -> blocked triangular
  *          solve against L -> predictive mean and variance.  beta and Kx never reach HBM as
  *          N x M matrices.            (OPT:535 cand_cross, OPT:544 beta, OPT:547-548 func_m/func_v)

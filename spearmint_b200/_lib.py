@@ -51,6 +51,8 @@ SIGNATURES = {
     "smk_predict_workspace_bytes": ([_i, _i], _sz),
     "smk_topk_workspace_bytes": ([_i, _i], _sz),
     "smk_ei_over_hypers_host_f32": ([_i, _i, _i, _i, _i] + [_p] * 9, _i),
+    "smk_potrf_loglik_workspace_bytes": ([_i, _i], _sz),
+    "smk_potrf_loglik_f64": ([_i, _i, _p, _p, _sz, _p, _i, _p], _i),
     "smk_tc_np": ([_i], _i),
     "smk_trtri_workspace_bytes": ([_i, _i], _sz),
     "smk_trtri_split_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p], _i),

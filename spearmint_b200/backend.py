@@ -60,29 +60,51 @@ class DeviceBackend(object):
             st.args = (comp, pend, vals, normals, durs_log)
         chunk = eng.max_samples_per_chunk(_ceil(comp.shape[0] + P, 128), _ceil(200000, 128), F)
         st.preps = None
-        if st.hs and len(st.hs) <= chunk:            # everything resident: prepare once, sweep many
-            st.preps = eng.prepare(kind, st.hs, comp, pend, vals, normals, st.ths, durs_log)
-            st.preps.fac.check_pd()
+        err = None
+        try:
+            if st.hs and len(st.hs) <= chunk:        # everything resident: prepare once, sweep many
+                st.preps = eng.prepare(kind, st.hs, comp, pend, vals, normals, st.ths, durs_log)
+                st.preps.fac.check_pd()
+        except np.linalg.LinAlgError as e:           # the reference lets spla.cholesky raise; so do we --
+            err = e                                  # on every rank, or the others would hang in the all-reduce
+        parallel.agree_on_error(err, eng.device)
         return st
 
     def _local(self, st, cand, want_matrix):
+        """This rank's EI (matrix and sum over its hyper-samples).  Every rank ends with the same single
+        agree_on_error() collective, whatever path it took (resident factors, chunked, empty shard)."""
         eng = self.eng32
         ldm = _ceil(cand.shape[0], 128)
+        err, ei, ei_sum = None, None, None
         if not st.hs:
-            return None, torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
-        if st.preps is not None:
-            return eng.ei_prepared(st.preps, eng.to_dev(cand), want_matrix, None)
-        comp, pend, vals, normals, durs_log = st.args
-        ei, ei_sum, _ = eng.ei_over_hypers_device(st.kind, st.hs, comp, pend, cand, vals, normals, st.ths, durs_log,
-                                                  want_matrix=want_matrix)
+            ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
+        elif st.preps is not None:
+            ei, ei_sum = eng.ei_prepared(st.preps, eng.to_dev(cand), want_matrix, None)
+        else:
+            comp, pend, vals, normals, durs_log = st.args
+            try:                                     # chunked path: factors are (re)built per pass and may raise here
+                ei, ei_sum, _ = eng.ei_over_hypers_device(st.kind, st.hs, comp, pend, cand, vals, normals, st.ths,
+                                                          durs_log, want_matrix=want_matrix)
+            except np.linalg.LinAlgError as e:
+                err = e
+        parallel.agree_on_error(err, eng.device)
         return ei, ei_sum
+
+    def _tail_fix(self, st, cand, ei, ei_sum, M):
+        """float64 re-evaluation of the short-list when the pass is in the deep-tail regime (engine.tail_fix)."""
+        comp, pend, vals, normals, durs_log = st.args
+        return self.eng32.tail_fix(st.kind, st.hs, st.S, comp, pend, cand, vals, normals, st.ths, durs_log, ei, ei_sum, M,
+                                   reduce_fn=parallel.allreduce_sum_)
 
     def ei_matrix(self, st, cand):
         M = cand.shape[0]
-        ei, _ = self._local(st, cand, True)
+        ei, ei_sum = self._local(st, cand, True)
         rank, world = parallel.world()
         if world == 1:
+            self._tail_fix(st, cand, ei, ei_sum, M)
             return ei[:, :M].t().contiguous().double().cpu().numpy()
+        parallel.allreduce_sum_(ei_sum)
+        self._tail_fix(st, cand, ei, ei_sum, M)      # the same decision on every rank (global sum); local columns fixed
         full = torch.zeros((st.S, _ceil(M, 128)), dtype=torch.float64, device=self.eng32.device)
         if ei is not None:
             full[st.mine] = ei
@@ -93,6 +115,7 @@ class DeviceBackend(object):
         M = cand.shape[0]
         _, ei_sum = self._local(st, cand, False)
         parallel.allreduce_sum_(ei_sum)              # the single exchange of the path
+        self._tail_fix(st, cand, None, ei_sum, M)    # deep-tail passes: exact float64 ranking of the short-list
         idx, _ = self.eng32.topk(ei_sum, M, k)       # argsort / argmax of the mean == of the sum
         return idx.cpu().numpy().astype(int)
 

@@ -18,6 +18,7 @@ factors the 20 refinements are cheap.  Extra optional keys: ``device``, ``refine
 import os
 import pickle
 import tempfile
+import time
 
 import numpy as np
 import numpy.random as npr
@@ -164,6 +165,13 @@ class GPEIOptChooserB200(object):
             raise NotImplementedError("mcmc_iters=0 (ML-II hyper-parameters) is broken in the reference "
                                       "(GPEIOptChooser.py:316-318) and not provided here")
 
+        t_phase = [time.perf_counter()]
+        phase_ms = {}
+
+        def lap(name):          # wall-clock split of next(): every phase ends in a host read, so perf_counter is exact
+            t_phase.append(time.perf_counter())
+            phase_ms[name] = phase_ms.get(name, 0.0) + 1e3 * (t_phase[-1] - t_phase[-2])
+
         self._loglik = self.backend.loglik(self.covar, comp, vals)
         if self.needs_burnin:
             for mcmc_iter in range(self.burnin):
@@ -180,7 +188,10 @@ class GPEIOptChooserB200(object):
                 % (mcmc_iter + 1, self.mcmc_iters, self.mean, np.sqrt(self.amp2), self.noise,
                    np.min(self.ls), np.max(self.ls)))
         self.dump_hypers()
+        self.stats["loglik_evals"] = getattr(self._loglik, "calls", None)
+        self.stats["loglik_batches"] = getattr(self._loglik, "launch_batches", None)
         self._loglik = None
+        lap("mcmc")
 
         b = [(0, 1)] * cand.shape[1]       # optimization bounds
 
@@ -188,6 +199,7 @@ class GPEIOptChooserB200(object):
         state = self._grid_state(comp, pend, vals)
         inds = self.backend.top_mean_ei(state, cand2, min(self.grid_subset, cand2.shape[0]))
         cand2 = cand2[inds, :]
+        lap("grid_pass_1")
 
         # refine each of them with L-BFGS-B on the (summed) EI (OPT:274-291), factors cached
         ctx = self._refine_context(comp, pend, vals)
@@ -198,10 +210,13 @@ class GPEIOptChooserB200(object):
         cand = np.vstack((cand, cand2))
         self.stats["refine_evals"] = getattr(ctx, "evals", None)
         del ctx
+        lap("refine")
 
         # grid pass 2 (OPT:293-294): argmax of the mean EI over grid + refined points
         best_cand = int(self.backend.top_mean_ei(state, cand, 1)[-1])
         self._set_current(self.hyper_samples[-1])      # ei_over_hypers leaves the last sample loaded (OPT:334-338)
+        lap("grid_pass_2")
+        self.stats["phase_ms"] = phase_ms
 
         if best_cand >= numcand:
             return (int(numcand), cand[best_cand, :])

@@ -15,6 +15,7 @@ static std::atomic<long long> g_launches{0};
 static char g_err[512] = "";
 
 void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches.load(); }
 
 // ---- optional kernel timing: (name, start, stop) event triples recorded around selected launches
 struct TimedSpan { const char* name; cudaEvent_t e0, e1; };
@@ -85,6 +86,8 @@ int predict_tc(int, int, int, int, int, int, const float*, const float*, const f
                const __half*, const __half*, const int*, const float*, int, float*, float*, int, void*, size_t, float*,
                int, const float*, float*, cudaStream_t);
 size_t predict_workspace_bytes_any(int, int);
+size_t potrf_ll_workspace_bytes(int, int);
+int potrf_ll_f64(int, int, double*, double*, int*, int, cudaStream_t);
 
 }  // namespace smk
 
@@ -133,6 +136,13 @@ int smk_potrf_lower_batched_f32(int Npad, int S, float* A, float* winv, int* inf
 }
 int smk_potrf_lower_batched_f64(int Npad, int S, double* A, double* winv, int* info, void* stream) {
   return potrf_lower_batched<double>(Npad, S, A, winv, info, ST(stream));
+}
+
+size_t smk_potrf_loglik_workspace_bytes(int Npad, int S) { return potrf_ll_workspace_bytes(Npad, S); }
+int smk_potrf_loglik_f64(int Npad, int S, double* A, void* workspace, size_t workspace_bytes, int* info, int use_graph,
+                         void* stream) {
+  if (!workspace || workspace_bytes < potrf_ll_workspace_bytes(Npad, S)) return -4;
+  return potrf_ll_f64(Npad, S, A, reinterpret_cast<double*>(workspace), info, use_graph, ST(stream));
 }
 
 int smk_chol_solve_f32(int N, int Npad, int S, int F, const float* L, const float* winv, const float* y,

@@ -216,6 +216,7 @@ __device__ __forceinline__ T kernel_of_r2(int kind, T r2) {
 
 // launch bookkeeping (api.cu)
 void count_launch(int n = 1);
+long long launch_count();
 int check_launch(const char* what);
 // optional per-kernel CUDA-event timing on the launch stream (bench.py's roofline leg): no-ops unless enabled
 void timing_begin(const char* name, cudaStream_t st);

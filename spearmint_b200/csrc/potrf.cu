@@ -8,159 +8,22 @@
 //   trailing : A_IK -= L_Ij * L_Kj^T   for I >= K > j     (block SYRK/GEMM)
 // The trailing update carries N^3/3 of the flops and is the tensor-core candidate.
 #include "common.cuh"
+#include "diag.cuh"
 
 namespace smk {
 
 // ------------------------------------------------------------------------------------------ diag
-// Factor one NB x NB diagonal block and invert its factor, entirely on one SM (this kernel is the serial spine of
-// the factorisation: nblk launches per matrix, so its latency -- not its flops -- is what matters, above all for
-// the one-matrix-at-a-time log-likelihood calls of the slice sampler).
-//   for each 32-wide sub-block:  (a) factor the 32 x 32 diagonal piece and invert it (block_chol_inv_32);
-//   (b) rows below: X = A_sub * Wdd^T;  (c) rank-32 update of what is left.
-//   Then W = L^-1 is assembled from the 32 x 32 inverses by block distance (d = 1, 2, ...).
-template <typename T>
-__device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-// The whole block (256 threads) factors the 32x32 SPD piece at `a` (row stride lda, lower part) in place and writes its
-// inverse into `w`.  One column (resp. one row of the inverse) per step, a few elements per thread, block barriers in
-// between: the per-step latency is a barrier plus one shared-memory round trip (~100-150 cycles) instead of a
-// 30-iteration dependent loop in a single warp.  `red` is a [8][32] scratch.
-template <typename T>
-__device__ __forceinline__ void block_chol_inv_32(T* a, int lda, T* w, int ldw, T* red, int tid, int& bad) {
-  for (int j = 0; j < 32; ++j) {
-    T d = a[j * lda + j];
-    if (!(d > T(0))) { if (bad < 0) bad = j; d = T(1); }
-    const T piv = smk_sqrt(d), ipiv = T(1) / piv;
-    __syncthreads();                               // everybody has read the pivot
-    if (tid == j) a[j * lda + j] = piv;
-    else if (tid > j && tid < 32) a[tid * lda + j] *= ipiv;
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {                  // rank-1 update of the trailing lower triangle (<= 496 elements)
-      const int e = tid + q * 256, i = e >> 5, k = e & 31;
-      if (k > j && k <= i) a[i * lda + k] = fma(-a[i * lda + j], a[k * lda + j], a[i * lda + k]);
-    }
-    __syncthreads();
-  }
-  // inverse by rows: W[i][c] = (delta_ic - sum_{c<=k<i} L[i][k] W[k][c]) / L[i][i], k split over 8 thread groups
-  const int c = tid & 31, part = tid >> 5;
-  for (int i = 0; i < 32; ++i) {
-    T acc = T(0);
-    for (int k = c + part; k < i; k += 8) acc = fma(a[i * lda + k], w[k * ldw + c], acc);
-    red[part * 32 + c] = acc;
-    __syncthreads();
-    if (part == 0) {
-      T sum = T(0);
-#pragma unroll
-      for (int g = 0; g < 8; ++g) sum += red[g * 32 + c];
-      w[i * ldw + c] = (c <= i) ? (((c == i) ? T(1) : T(0)) - sum) / a[i * lda + i] : T(0);
-    }
-    __syncthreads();
-  }
-}
-
+// Factor one NB x NB diagonal block and invert its factor, entirely on one SM (diag.cuh).  This kernel is the serial
+// spine of the factorisation: nblk launches per matrix, so its latency -- not its flops -- is what matters.
 template <typename T>
 __global__ void __launch_bounds__(256) potrf_diag_kernel(int Npad, int jb, T* __restrict__ A,
                                                           T* __restrict__ winv, int* __restrict__ info) {
-  constexpr int NB = Cfg<T>::NB, SB = 32, NSB = NB / SB;
-  constexpr int LDS = NB + 1;
+  constexpr int NB = Cfg<T>::NB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* a = reinterpret_cast<T*>(smem_raw);   // [NB][LDS] block being factored (lower)
-  T* w = a + NB * LDS;                     // [NB][LDS] its inverse (lower)
-  T* t = w + NB * LDS;                     // [NB][SB+1] scratch for the panel / inverse assembly
-  constexpr int LDT = SB + 1;
-  const int s = blockIdx.x, tid = threadIdx.x;
+  const int s = blockIdx.x;
   T* Ab = A + (long)s * Npad * Npad + (long)jb * NB * Npad + (long)jb * NB;
-
-  for (int e0 = tid; e0 < NB * NB; e0 += 256 * 8) {
-    T v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      int e = e0 + q * 256, i = e / NB, k = e % NB;
-      v[q] = (e < NB * NB && k <= i) ? Ab[(long)i * Npad + k] : T(0);
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      int e = e0 + q * 256, i = e / NB, k = e % NB;
-      if (e < NB * NB) { a[i * LDS + k] = v[q]; w[i * LDS + k] = T(0); }
-    }
-  }
-  __syncthreads();
-
-  for (int sb = 0; sb < NSB; ++sb) {
-    const int o = sb * SB;
-    // (a) 32x32 diagonal piece: factor + invert
-    {
-      int bad = -1;
-      block_chol_inv_32<T>(a + o * LDS + o, LDS, w + o * LDS + o, LDS, t, tid, bad);
-      if (bad >= 0 && tid == 0 && info[s] == 0) info[s] = jb * NB + o + bad + 1;
-    }
-    __syncthreads();
-    const int rows = NB - o - SB;                    // rows below the diagonal piece
-    if (rows > 0) {
-      // (b) X[r][k] = sum_{m<=k} A[r][o+m] * Wdd[k][m]   -> scratch, then back into a
-      for (int e = tid; e < rows * SB; e += 256) {
-        int rr = e / SB, k = e % SB;
-        const T* ar = a + (o + SB + rr) * LDS + o;
-        const T* wk = w + (o + k) * LDS + o;
-        T acc = T(0);
-        for (int m = 0; m <= k; ++m) acc = fma(ar[m], wk[m], acc);
-        t[rr * LDT + k] = acc;
-      }
-      __syncthreads();
-      for (int e = tid; e < rows * SB; e += 256) {
-        int rr = e / SB, k = e % SB;
-        a[(o + SB + rr) * LDS + o + k] = t[rr * LDT + k];
-      }
-      // (c) rank-32 update of the remaining lower triangle: a[r][c] -= X[r] . X[c]   (r >= c)
-      for (int e = tid; e < rows * rows; e += 256) {
-        int rr = e / rows, cc = e % rows;
-        if (cc > rr) continue;
-        const T* xr = t + rr * LDT;
-        const T* xc = t + cc * LDT;
-        T acc = a[(o + SB + rr) * LDS + o + SB + cc];
-#pragma unroll 8
-        for (int k = 0; k < SB; ++k) acc = fma(-xr[k], xc[k], acc);
-        a[(o + SB + rr) * LDS + o + SB + cc] = acc;
-      }
-      __syncthreads();
-    }
-  }
-
-  // W = L^-1: off-diagonal 32x32 blocks by block distance d:  W_ij = -W_ii * (sum_{k=j}^{i-1} L_ik W_kj)
-  for (int d = 1; d < NSB; ++d) {
-    const int npair = NSB - d;                       // (i, j) = (j + d, j)
-    // phase 1: T_ij = sum_k L_ik W_kj  into scratch t[(pair*32 + r)][c]
-    for (int e = tid; e < npair * SB * SB; e += 256) {
-      int pr = e / (SB * SB), rr = (e / SB) % SB, cc = e % SB;
-      int j = pr, i = pr + d;
-      T acc = T(0);
-      for (int kb = j; kb < i; ++kb) {
-        const T* lrow = a + (i * SB + rr) * LDS + kb * SB;
-#pragma unroll 8
-        for (int m = 0; m < SB; ++m) acc = fma(lrow[m], w[(kb * SB + m) * LDS + j * SB + cc], acc);
-      }
-      t[(pr * SB + rr) * LDT + cc] = acc;
-    }
-    __syncthreads();
-    // phase 2: W_ij = -W_ii * T_ij
-    for (int e = tid; e < npair * SB * SB; e += 256) {
-      int pr = e / (SB * SB), rr = (e / SB) % SB, cc = e % SB;
-      int j = pr, i = pr + d;
-      const T* wrow = w + (i * SB + rr) * LDS + i * SB;
-      T acc = T(0);
-      for (int m = 0; m <= rr; ++m) acc = fma(wrow[m], t[(pr * SB + m) * LDT + cc], acc);
-      w[(i * SB + rr) * LDS + j * SB + cc] = -acc;
-    }
-    __syncthreads();
-  }
-
   T* Wb = winv + ((long)s * (Npad / NB) + jb) * NB * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
-    int i = e / NB, k = e % NB;
-    if (k <= i) Ab[(long)i * Npad + k] = a[i * LDS + k];
-    Wb[e] = w[i * LDS + k];
-  }
+  diag_factor_block<T, NB>(Ab, Npad, Wb, info + s, jb * NB, reinterpret_cast<T*>(smem_raw));
 }
 
 // ------------------------------------------------------------------------------------------ panel
@@ -252,7 +115,7 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
   if (!winv) return -4;
   if (!info) return -5;
   const int nblk = Npad / NB;
-  const size_t dsm = (2 * (size_t)NB * (NB + 1) + (size_t)NB * 33) * sizeof(T);
+  const size_t dsm = DiagSmem<T, NB>::bytes;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
@@ -291,7 +154,7 @@ int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, fl
   if (S <= 0) return -2;
   if (!A || !winv || !info || !lhi || !llo) return -3;
   const int nblk = Npad / NB;
-  const size_t dsm = (2 * (size_t)NB * (NB + 1) + (size_t)NB * 33) * sizeof(float);
+  const size_t dsm = DiagSmem<float, NB>::bytes;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(potrf_diag_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);

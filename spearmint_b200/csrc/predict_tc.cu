@@ -975,7 +975,14 @@ static int tc_nbuf(int Np, int M, int S, size_t budget) {
   if (!tc_overlap_enabled()) return 1;
   return tc_chunk_cands(Np, M, S, budget) >= mpad ? 1 : 2;
 }
-static const size_t kTcBudget = (size_t)20 << 30;
+// Operand-chunk budget: 20 GB of cross-covariance per candidate chunk.  SMK_TC_BUDGET_MB overrides it (tests use a
+// small value to push a few thousand candidates through the multi-chunk + ragged-tail path of the headline shape).
+static size_t tc_budget() {
+  const char* e = getenv("SMK_TC_BUDGET_MB");
+  if (e && e[0]) { long mb = atol(e); if (mb > 0) return (size_t)mb << 20; }
+  return (size_t)20 << 30;
+}
+#define kTcBudget (tc_budget())
 
 static int fant_rows(int F) { return F > 1 ? ((F + tc::BN - 1) / tc::BN) * tc::BN : 0; }
 

@@ -65,20 +65,33 @@ class Factor(object):
         self.Npad = _ceil(self.N, 128)
         S, dt, dev = hb.S, eng.dtype, eng.device
         NB = eng.NB
-        self.L = L if L is not None else torch.empty((S, self.Npad, self.Npad), dtype=dt, device=dev)
-        self.winv = winv if winv is not None else torch.empty((S, self.Npad // NB, NB, NB), dtype=dt, device=dev)
+        self._owned = []
+        self.L = L if L is not None else self._take((S, self.Npad, self.Npad))
+        self.winv = winv if winv is not None else self._take((S, self.Npad // NB, NB, NB))
         self.info = info if info is not None else torch.zeros((S,), dtype=torch.int32, device=dev)
         st = eng.stream()
         check(fn("smk_cov_build", dt)(KINDS[kind], self.N, self.N, self.D, S, ptr(X), None, ptr(hb.inv_ls),
                                       ptr(hb.amp2), ptr(hb.noise), ptr(self.L), self.Npad, st), "cov_build")
         if eng.factor_impl == "tc" and dt == torch.float32 and self.Npad >= 256:
             nb = 2 * S * self.Npad * self.Npad * 4
-            ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+            ws = eng.take((nb,), torch.uint8)
+            eng.give(ws)                      # scratch of this call only (stream-ordered reuse)
             check(_lib.lib().smk_potrf_lower_batched_tc_f32(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info),
                                                             ptr(ws), nb, st), "potrf_tc")
         else:
             check(fn("smk_potrf_lower_batched", dt)(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info), st),
                   "potrf")
+
+    def _take(self, shape, dtype=None):
+        t = self.eng.take(shape, dtype)
+        self._owned.append(t)
+        return t
+
+    def __del__(self):
+        try:
+            self.eng.give(*self._owned)      # back to the engine's free list; later work is stream-ordered behind ours
+        except Exception:
+            pass
 
     def linv(self):
         """(hi, lo, Np): explicit inverse of the factor as a tf32 hi/lo pair of float32 arrays; computed once."""
@@ -86,16 +99,18 @@ class Factor(object):
             eng, L = self.eng, _lib.lib()
             S = self.hb.S
             Np = L.smk_tc_np(self.N)
-            hi = torch.empty((S, Np, Np), dtype=torch.float32, device=eng.device)
-            lo = torch.empty((S, Np, Np), dtype=torch.float32, device=eng.device)
+            hi = self._take((S, Np, Np), torch.float32)
+            lo = self._take((S, Np, Np), torch.float32)
             if eng.factor_impl == "tc" and self.Npad >= 256:
                 nb = L.smk_trtri_tc_workspace_bytes(self.Npad, Np, S)
-                ws = torch.empty((nb,), dtype=torch.uint8, device=eng.device)
+                ws = eng.take((nb,), torch.uint8)
+                eng.give(ws)
                 check(L.smk_trtri_split_tc_f32(self.Npad, Np, S, ptr(self.L), ptr(self.winv), ptr(hi), ptr(lo), ptr(ws),
                                                nb, eng.stream()), "trtri_split_tc")
             else:
                 nb = L.smk_trtri_workspace_bytes(Np, S)
-                ws = torch.empty((nb,), dtype=torch.uint8, device=eng.device)
+                ws = eng.take((nb,), torch.uint8)
+                eng.give(ws)
                 check(L.smk_trtri_split_f32(self.Npad, Np, S, ptr(self.L), ptr(self.winv), ptr(hi), ptr(lo), ptr(ws),
                                             nb, eng.stream()), "trtri_split")
             self._linv = (hi, lo, Np)
@@ -108,8 +123,8 @@ class Factor(object):
             eng, L = self.eng, _lib.lib()
             hi, lo, Np = self.linv()
             S = self.hb.S
-            h16 = torch.empty((S, Np, Np), dtype=torch.float16, device=eng.device)
-            l16 = torch.empty((S, Np, Np), dtype=torch.float16, device=eng.device)
+            h16 = self._take((S, Np, Np), torch.float16)
+            l16 = self._take((S, Np, Np), torch.float16)
             exps = torch.empty((2 * S,), dtype=torch.int32, device=eng.device)
             check(L.smk_linv_pack_f16(Np, S, ptr(hi), ptr(lo), ptr(h16), ptr(l16), ptr(exps), eng.stream()),
                   "linv_pack_f16")
@@ -188,6 +203,42 @@ class GPEIEngine(object):
         self.factor_impl = os.environ.get("SMK_FACTOR_IMPL", "tc" if self.predict_impl == "tc" else "simt")
         self.last = {}
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
+        self._pool = {}      # (shape, dtype) -> free tensors: the big per-call buffers are recycled, never re-allocated
+        self._helper64 = None
+
+    # ------------------------------------------------------------------ buffers
+    def take(self, shape, dtype=None):
+        """A device buffer of exactly this shape from the engine's free list (allocated on first use only).  The C library
+        never allocates; this is the host-side mirror of that rule: steady-state calls reuse the same HBM."""
+        key = (tuple(int(x) for x in shape), dtype or self.dtype)
+        free = self._pool.get(key)
+        if free:
+            return free.pop()
+        try:
+            return torch.empty(key[0], dtype=key[1], device=self.device)
+        except torch.cuda.OutOfMemoryError:
+            self.trim()                       # buffers of other shapes are the only thing the pool can be blamed for
+            return torch.empty(key[0], dtype=key[1], device=self.device)
+
+    def trim(self):
+        self._pool.clear()
+        torch.cuda.empty_cache()
+
+    def pooled_bytes(self):
+        return sum(t.numel() * t.element_size() for v in self._pool.values() for t in v)
+
+    def give(self, *tensors):
+        for t in tensors:
+            if t is not None:
+                self._pool.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+    def helper64(self):
+        """The float64 engine on the same device (pending-point conditionals, deep-tail re-evaluation)."""
+        if self.dtype == torch.float64:
+            return self
+        if self._helper64 is None:
+            self._helper64 = GPEIEngine(device=self.device, dtype=torch.float64)
+        return self._helper64
 
     # ------------------------------------------------------------------ timing helpers
     def _t0(self):
@@ -228,6 +279,7 @@ class GPEIEngine(object):
         sample, capped by the library's 20 GB chunk budget)."""
         free, _ = torch.cuda.mem_get_info(self.device)
         free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        free += self.pooled_bytes()           # recycled (or dropped by take() on demand)
         budget = 0.7 * free
         per = self.esize * (Npad * Npad + Npad * self.NB + F * Npad + (F + 3) * ldm)
         if self.predict_impl == "tc" and self.dtype == torch.float32:
@@ -360,29 +412,36 @@ class GPEIEngine(object):
             p.bests_host = np.full((hb.S, 1), best_val)
             p.pred_alpha = alpha.view(hb.S, fac.Npad)
         else:
-            self._prepare_pending(p, kind, hb, Xo, self.to_dev(pend), yd, np.asarray(vals, float),
-                                  np.asarray(normals, float))
+            if comp is None:
+                raise _lib.SmkError("pending points need the host arrays (comp, pend, vals), not resident tensors")
+            self._prepare_pending(p, kind, hb, hyper_samples, Xo, self.to_dev(pend), yd, np.asarray(comp, float),
+                                  np.asarray(pend, float), np.asarray(vals, float), np.asarray(normals, float))
         return p
 
-    def _prepare_pending(self, p, kind, hb, Xo, Pd, yd, vals, normals):
+    def _prepare_pending(self, p, kind, hb, hyper_samples, Xo, Pd, yd, comp, pend, vals, normals):
         """Pending-fantasy prologue (OPT:558-603) for one chunk of hyper-samples.
 
-        The joint (N+P) factor and all big solves run on the device; the P x P conditional of the pending points
-        (P <= max_concurrent, a handful) and the fantasy draw use the host in float64 with the caller's normals, so
-        the host RNG order is the reference's."""
+        The P x P conditional of the pending points (pend_m, pend_K, OPT:577-585) is formed from a FLOAT64 joint
+        factor: pend_K = Lpp Lpp' - noise I cancels down to the 1e-6 amp2 jitter when a pending point sits next to an
+        observation (the 1e-3 jitter cloud next() itself proposes) or duplicates another pending point, and float32
+        rounding of the joint factor is of that order -- the reference's float64 succeeds there, so must we.  The
+        fantasy draw uses the host with the caller's normals (the host RNG order is the reference's).  The float32
+        joint factor of the grid path and the F fantasy right-hand sides stay on the float32 engine."""
         N, P, F = Xo.shape[0], Pd.shape[0], normals.shape[-1]
         S = hb.S
         per_sample = (normals.ndim == 3)     # (S,P,F): GPEIChooser draws fresh normals per hyper-sample (GPEI:237)
-        Xj = torch.cat([Xo, Pd], dim=0).contiguous()
-        fac = self.factor(kind, Xj, hb)
-        fac.check_pd()
+        h64 = self.helper64()
+        hb64 = hb if h64 is self else h64.hypers(hyper_samples, kind)
+        Xo64, Pd64 = h64.to_dev(comp), h64.to_dev(pend)
+        Xj64 = torch.cat([Xo64, Pd64], dim=0).contiguous()
+        fac64 = h64.factor(kind, Xj64, hb64)
+        fac64.check_pd()                                       # LinAlgError like OPT:567
         # alpha of the observed-only system from the leading N x N block of the joint factor (OPT:574-577)
-        a_obs, _, _ = fac.solve(yd, F=1, n_lead=N)
+        a_obs, _, _ = fac64.solve(h64.to_dev(vals), F=1, n_lead=N)
         # pend_m = pend_cross' alpha + mean (OPT:581): cross mean of the observed set at the P pending points
-        ofac = _LeadingView(fac, Xo, N)
-        pend_m = self.cross_mean(kind, ofac, Pd, a_obs, 1)[:, 0, :P].double().cpu().numpy()          # (S,P)
+        pend_m = h64.cross_mean(kind, _LeadingView(fac64, Xo64, N), Pd64, a_obs, 1)[:, 0, :P].cpu().numpy()   # (S,P)
         # pend_K = Schur complement - noise I, from the trailing P x P block of the joint factor (OPT:582)
-        Lpp = fac.L[:, N:N + P, N:N + P].double().cpu().numpy()
+        Lpp = fac64.L[:, N:N + P, N:N + P].cpu().numpy()
         fant = np.empty((S, F, N + P))
         bests = np.empty((S, F))
         for s in range(S):
@@ -393,6 +452,12 @@ class GPEIEngine(object):
             fant[s, :, :N] = vals[None, :]
             fant[s, :, N:] = pf.T
             bests[s] = np.minimum(vals.min(), pf.min(axis=0))                     # OPT:597
+        if h64 is self:
+            fac = fac64
+        else:
+            del fac64
+            fac = self.factor(kind, torch.cat([Xo, Pd], dim=0).contiguous(), hb)
+            fac.check_pd()
         fant_d = self.to_dev(fant)                                                # [S][F][N+P]
         alpha_f, _, _ = fac.solve(fant_d, F=F, y_stride=F * (N + P), ldy=N + P)   # OPT:603
         p.fac, p.alpha, p.F = fac, alpha_f, F
@@ -459,9 +524,45 @@ class GPEIEngine(object):
     def ei_over_hypers(self, kind, hyper_samples, comp, pend, cand, vals, normals=None,
                        time_hyper_samples=None, durs_log=None):
         """Host-facing: numpy in, (M,S) float64 numpy out -- the reference's ei_over_hypers contract (OPT:331-341)."""
-        ei, _, M = self.ei_over_hypers_device(kind, hyper_samples, comp, pend, cand, vals, normals,
-                                              time_hyper_samples, durs_log, want_matrix=True)
+        ei, ei_sum, M = self.ei_over_hypers_device(kind, hyper_samples, comp, pend, cand, vals, normals,
+                                                   time_hyper_samples, durs_log, want_matrix=True)
+        self.tail_fix(kind, hyper_samples, len(hyper_samples), comp, pend, cand, vals, normals, time_hyper_samples,
+                      durs_log, ei, ei_sum, M)
         return ei[:, :M].t().contiguous().double().cpu().numpy()
+
+    # ------------------------------------------------------------------ deep-tail regime: exact ranking of the short-list
+    TAIL_MEAN_EI = 1e-6      # below this max mean-EI the float32 moments no longer rank candidates like the reference
+    TAIL_SHORTLIST = 256
+
+    def tail_fix(self, kind, hs_local, S_total, comp, pend, cand, vals, normals, ths_local, durs_log, ei, ei_sum, M,
+                 reduce_fn=None):
+        """Late in a run max EI is 1e-8 ... 1e-60: EI = s (u Phi(u) + phi(u)) depends exponentially on u = (best - mu) / s,
+        and float32 predictive moments then carry tens of percent of relative error -- enough to reorder the top of the
+        ranking, while the reference (float64) proposes its exact argmax (OPT:294).  When the largest mean EI of a pass is
+        below TAIL_MEAN_EI, the TAIL_SHORTLIST best candidates of the float32 ranking are re-evaluated with the float64
+        build of the same kernels and their EI (per sample and summed) replaces the float32 values, so the argmax / top-k
+        are decided in float64 exactly like the reference's.  ``ei_sum`` must already be the global (all-reduced) sum;
+        ``reduce_fn`` all-reduces the short-list sums in place when hyper-samples are sharded over ranks."""
+        if self.dtype != torch.float32:
+            return False
+        top = float(ei_sum[:M].max())                       # one scalar read; the caller synchronises right after anyway
+        if not (top < self.TAIL_MEAN_EI * S_total):
+            return False
+        k = min(self.TAIL_SHORTLIST, M)
+        idx, _ = self.topk(ei_sum, M, k)
+        idx_h = idx.cpu().numpy().astype(np.int64)
+        sub = torch.zeros((k,), dtype=torch.float64, device=self.device)
+        if hs_local:
+            h64 = self.helper64()
+            e64, s64, _ = h64.ei_over_hypers_device(kind, hs_local, comp, pend, np.ascontiguousarray(cand[idx_h]), vals,
+                                                    normals, ths_local, durs_log, want_matrix=True)
+            sub += s64[:k]
+            if ei is not None:
+                ei[:, idx.long()] = e64[:, :k]
+        if reduce_fn is not None:
+            reduce_fn(sub)
+        ei_sum[idx.long()] = sub
+        return True
 
     # ------------------------------------------------------------------ f2: GP log marginal likelihood
     def loglik(self, kind, comp, vals):
@@ -486,12 +587,20 @@ class LogLik(object):
         self.y = eng.to_dev(vals)
         self.N, self.D = self.X.shape
         self.Npad = _ceil(self.N + 1, 128)          # room for the augmented row
-        if max_batch is None:      # batching pays while the factorisation is latency-bound
-            max_batch = 8 if self.N <= 1024 else (6 if self.N <= 2048 else 4)
+        if max_batch is None:      # one slice move = 3 + SPECULATE points (util.py); small N is pure launch latency
+            max_batch = 8 if self.N <= 1024 else 6
         self.max_batch = max_batch
         dt, dev = eng.dtype, eng.device
         self.L = torch.empty((max_batch, self.Npad, self.Npad), dtype=dt, device=dev)
-        self.winv = torch.empty((max_batch, self.Npad // eng.NB, eng.NB, eng.NB), dtype=dt, device=dev)
+        # float64: dedicated look-ahead / DMMA factorisation (csrc/potrf_ll.cu); its workspace holds the inverse diagonal
+        # blocks.  float32 (tests only): the generic blocked factorisation.
+        self.fast = (dt == torch.float64) and os.environ.get("SMK_LOGLIK_IMPL", "ll") == "ll"
+        self.use_graph = 1 if os.environ.get("SMK_LOGLIK_GRAPH", "1") == "1" else 0
+        if self.fast:
+            self.ws_bytes = _lib.lib().smk_potrf_loglik_workspace_bytes(self.Npad, max_batch)
+            self.winv = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+        else:
+            self.winv = torch.empty((max_batch, self.Npad // eng.NB, eng.NB, eng.NB), dtype=dt, device=dev)
         self.info = torch.zeros((max_batch,), dtype=torch.int32, device=dev)
         self.out = torch.empty((2, max_batch), dtype=dt, device=dev)
         self.calls = 0
@@ -509,7 +618,11 @@ class LogLik(object):
             check(fn("smk_cov_build", dt)(KINDS[self.kind], N, N, self.D, B, ptr(self.X), None, ptr(hb.inv_ls),
                                           ptr(hb.amp2), ptr(hb.noise), ptr(self.L), Npad, st), "cov_build")
             check(fn("smk_loglik_set_rhs", dt)(N, Npad, B, ptr(self.y), ptr(hb.mean), ptr(self.L), st), "loglik_set_rhs")
-            check(fn("smk_potrf_lower_batched", dt)(Npad, B, ptr(self.L), ptr(self.winv), ptr(self.info), st), "potrf")
+            if self.fast:
+                check(_lib.lib().smk_potrf_loglik_f64(Npad, B, ptr(self.L), ptr(self.winv), self.ws_bytes, ptr(self.info),
+                                                      self.use_graph, st), "potrf_loglik")
+            else:
+                check(fn("smk_potrf_lower_batched", dt)(Npad, B, ptr(self.L), ptr(self.winv), ptr(self.info), st), "potrf")
             check(fn("smk_loglik_finish", dt)(N, Npad, B, ptr(self.L), ptr(self.out[0]), ptr(self.out[1]), st),
                   "loglik_finish")
             r = torch.cat([self.out[0, :B].double(), self.out[1, :B].double(), self.info[:B].double()]).cpu().numpy()

@@ -28,6 +28,24 @@ def allreduce_sum_(t, group=None):
     return t
 
 
+def agree_on_error(exc, device="cpu", group=None):
+    """Raise on EVERY rank if any rank failed (e.g. a factorisation that is not positive definite in one rank's shard of
+    hyper-samples): a rank that raised alone would leave the others waiting in the EI all-reduce until the NCCL
+    timeout.  ``exc``: this rank's exception or None.  One 4-byte MAX all-reduce; a no-op for a single process."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        if exc is not None:
+            raise exc
+        return
+    import numpy as np
+    import torch
+    flag = torch.tensor([1 if exc is not None else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag[0]) != 0:
+        if exc is not None:
+            raise exc
+        raise np.linalg.LinAlgError("a hyper-sample owned by another rank is not positive definite")
+
+
 def sharded_mean_ei(local_ei_sum_fn, S, group=None):
     """mean_s EI[s, :] from per-rank partial sums.
 

@@ -90,7 +90,7 @@ def test_c_abi_host_entry_point():
 def test_ei_path_medium_n_vs_oracle(engines, D, N, M):
     """The golden fixtures stop at N = 64 (one factor block).  These sizes run the whole tensor-core chain --
     left-looking tcgen05 Cholesky (odd and even block counts), tcgen05 triangular inverse, 3xTF32 predict -- against
-    the float64 oracle with the same stated tolerance (|dEI| <= 5e-3 max EI, equal argmax unless the top-2 gap is inside it).
+    the float64 oracle with the same stated tolerance (|dEI| <= 5e-3 max EI) and EQUAL argmax of the mean EI.
     D=4 / N=600 is deliberately ill-conditioned (cond(K) ~ 1e6)."""
     from oracle import gp_oracle as O
     rs = np.random.RandomState(100 + D)
@@ -118,5 +118,5 @@ def test_ei_path_medium_n_vs_oracle(engines, D, N, M):
             assert int(np.argmax(r)) in set(np.argsort(e)[-5:])
         else:
             assert np.abs(e - r).max() <= 5e-3 * r.max(), (s, np.abs(e - r).max(), r.max())
-    return
-    _check(ei, ref, "f32")
+    # the proposal: argmax of the mean over samples (OPT:294) must be the reference's
+    assert int(np.argmax(ei.mean(axis=1))) == int(np.argmax(ref.mean(axis=1)))

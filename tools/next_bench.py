@@ -26,7 +26,7 @@ def problem(D, N, M):
     return grid, values, candidates, complete
 
 
-def run(backend_name, D, N, M, S, burnin, calls, grid_subset):
+def run(backend_name, D, N, M, S, burnin, calls, grid_subset, backend=None):
     from spearmint_b200.chooser import GPEIOptChooserB200 as mod
     import spearmint_b200.locker as lk
     lk.log = lambda *a: None
@@ -36,6 +36,8 @@ def run(backend_name, D, N, M, S, burnin, calls, grid_subset):
     if backend_name == "cpu":
         from tests.oracle_backend import OracleBackend
         ch._backend = OracleBackend()
+    elif backend is not None:
+        ch._backend = backend
     np.random.seed(0)
     out = []
     for c in range(calls):
@@ -48,7 +50,8 @@ def run(backend_name, D, N, M, S, burnin, calls, grid_subset):
             import torch
             torch.cuda.synchronize()
         out.append(dict(call=c, ms=1e3 * (time.perf_counter() - t0), ret=int(r[0] if isinstance(r, tuple) else r),
-                        refine_evals=ch.stats.get("refine_evals")))
+                        refine_evals=ch.stats.get("refine_evals"), loglik_evals=ch.stats.get("loglik_evals"),
+                        loglik_batches=ch.stats.get("loglik_batches"), phase_ms=ch.stats.get("phase_ms")))
     return out
 
 
