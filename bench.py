@@ -273,7 +273,9 @@ def run_b200_arm(args, D, N, M, S):
 
     def step_resident():
         if Sl:
-            _, ei_sum, _ = eng.ei_over_hypers_device(KIND, hs_local, None, None, None, None, want_matrix=False,
+            # compute reads the resident tensors; the host arrays ride along only for the accuracy guard's float64
+            # re-evaluation of flagged hyper-samples (none at the headline)
+            _, ei_sum, _ = eng.ei_over_hypers_device(KIND, hs_local, comp, None, cand, vals, want_matrix=False,
                                                      inputs_on_device=res, time_hyper_samples=ths_local, durs_log=durs)
         else:
             ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
@@ -401,7 +403,8 @@ def run_b200_arm(args, D, N, M, S):
                        "api": ("backend.grid_state + backend.ei_matrix (the calls GPEIperSecChooserB200 makes)" if per_s else
                                "GPEIOptChooserB200.ei_over_hypers(comp, pend, cand, vals)") +
                               " -> (M,S) float64 EI matrix on the host, host argmax of the mean"},
-               "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+               "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+               "accuracy_guard": dict(eng.last_guard or {}, threshold=eng.guard_threshold)}
         if world == 1 and not args.no_cpu:
             cpu = cpu_port_sample(args.workload, D, N, M, S, budget_cands=args.cpu_cands)
             out["cpu_baseline"] = {"value": cpu["value"], "unit": "candidates/s", "cores": cpu["threads"],

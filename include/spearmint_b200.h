@@ -146,6 +146,13 @@ int smk_trtri_split_tc_f32(int Npad, int Np, int S, const float* L, const float*
 /* alpha[s] = K_s^-1 (y - mean[s]) from the explicit inverse (two parallel mat-vecs; OPT:543); tmp: [S][Np] floats. */
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream);
+/* Accuracy guard of the tensor-core path (csrc/guard.cu): g[s] = estimated RELATIVE error of the predictive variance of a
+ * candidate sitting on an observed point, measured by pushing 4 columns of K = L L^T through the explicit inverse
+ * (float64 accumulation):  | |Linv (L v)|^2 - |v|^2 | / (noise + 1e-6 amp2),  v = a row of L.  The caller routes the
+ * batch to smk_predict_f32 (blocked substitution) when it exceeds its threshold.                                   */
+size_t smk_tc_guard_workspace_bytes(int Np, int S);
+int smk_tc_guard_f32(int N, int Npad, int Np, int S, const float* L, const float* linv_hi, const float* linv_lo,
+                     const float* amp2, const float* noise, float* g, void* workspace, size_t workspace_bytes, void* stream);
 size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F);
 /* F > 1 with alpha_f [S][F][Npad_alpha] and mu_f [S][F][ldm] non-NULL: additionally the fantasy means
  * mu_f[s][f][j] = cov(X, C_j)' alpha_f[s][f] + mean[s]  (OPT:609) as a second tcgen05 GEMM on the same Kxt chunk. */
@@ -189,10 +196,13 @@ int smk_cross_mean_f64(int kind, int N, int Npad, int M, int D, int S, int F, co
  * every candidate to zero (the reference ranks those tail values in float64).                              */
 int smk_ei_sweep_f32(int M, int S, int F, const float* mu, const float* var, int ldm,
                      const float* best, const float* log_time, double* ei, double* ei_sum,
-                     void* stream);
+                     unsigned long long* ei_max, void* stream);
 int smk_ei_sweep_f64(int M, int S, int F, const double* mu, const double* var, int ldm,
                      const double* best, const double* log_time, double* ei, double* ei_sum,
-                     void* stream);
+                     unsigned long long* ei_max, void* stream);
+/* ei_max (optional, [S]): receives the bit pattern of max_j EI[s][j] as a double (the engine's accuracy guard compares it
+ * with the error bound of the explicit-inverse path).  smk_ei_colsum: ei_sum[j] += sum_s ei[s][j].                    */
+int smk_ei_colsum(int M, int S, const double* ei, int ldm, double* ei_sum, void* stream);
 
 /* ---- (6) selection: argsort(mean)[-k:] and argmax(mean)   (OPT:270-271, OPT:294)
  * score: [M].  idx_out[k]: indices of the k largest scores in ASCENDING score order (so
@@ -227,6 +237,26 @@ int smk_ei_grad_terms_f32(int kind, int N, int Npad, int D, int S, int Q, int F,
 int smk_ei_grad_terms_f64(int kind, int N, int Npad, int D, int S, int Q, int F, const double* X, const double* xq,
                           const double* inv_ls, const double* amp2, const double* alpha, const double* gamma,
                           double* out, void* stream);
+
+/* ---- (8b) ML-II: the traces of GP.optimize_hypers' grad_nlogprob (GP:238-264) at one hyper-parameter setting per sample
+ * alpha: [S][lda] = K^-1 (y - mean);  Kinv: [S][N][ldk] = K^-1 (smk_chol_solve with the identity as right-hand sides).
+ * out: [S][D+2] doubles:  out[0] = sum_ij J_ij (corr_ij + 1e-6 delta_ij),  out[1] = tr J,
+ *                         out[2+d] = sum_ij J_ji gcorr_ij^d X[i][d],   J = alpha alpha' - K^-1  (GP:246).
+ * Host side: grad = [0.5 out[0] amp2, 0.5 out[1] noise, -amp2 out[2+d]] and grad_nlogprob = -grad -- including the
+ * reference's length-scale expression (GP:258-259), which is not the true derivative and is reproduced as is.        */
+int smk_mll_grad_terms_f32(int kind, int N, int D, int S, const float* X, const float* inv_ls, const float* alpha, int lda,
+                           const float* Kinv, int ldk, double* out, void* stream);
+int smk_mll_grad_terms_f64(int kind, int N, int D, int S, const double* X, const double* inv_ls, const double* alpha, int lda,
+                           const double* Kinv, int ldk, double* out, void* stream);
+
+/* ---- (9) Sobol candidate grid on the device: sobol_lib.i4_sobol_generate (spearmint/spearmint/sobol_lib.py:125-156,
+ *          called by ExperimentGrid GRID:192-196 and spearmint-lite LITE:171-173)
+ * out[j][d], j < n, d < D (row-major [n][D], i.e. the TRANSPOSE of the reference's (D, n) return value -- the layout
+ * its callers use): point of Gray-code seed max(skip + j - 1, 0).  V: device copy of the direction numbers [D][30]
+ * (spearmint_b200/data/sobol_v_1111x30.npy, frozen from the reference's Joe-Kuo table by tools/make_sobol_table.py).
+ * Returns -3 past the reference's 2^30 point limit.                                                               */
+int smk_sobol_generate_f32(int D, long long n, long long skip, const uint32_t* V, float* out, void* stream);
+int smk_sobol_generate_f64(int D, long long n, long long skip, const uint32_t* V, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -312,3 +312,56 @@ def grad_optimize_ei_per_s_over_hypers(kind, hyper_samples, time_hyper_samples, 
         fi, gi = grad_optimize_ei_per_s(kind, h, th, cand, comp, vals, durs_log)
         f, g = f + fi, g + gi
     return f, g
+
+
+# ----------------------------------------------------------------------------- ML-II hyper-parameters (GP.optimize_hypers)
+def jitter_chol(covmat):
+    """GP.optimize_hypers' jitter_chol (GP:187-203): lower Cholesky of covmat + jitter I, jitter = 1e-8 grown by 1.1x
+    until it factors; past 1e5 the factor of the identity.  Returns (chol, jitter_used)."""
+    jitter = 1e-8
+    while True:
+        if jitter > 100000:
+            return np.eye(covmat.shape[0]), jitter
+        try:
+            return spla.cholesky(covmat + jitter * np.eye(covmat.shape[0]), lower=True), jitter
+        except (ValueError, np.linalg.LinAlgError):
+            jitter = jitter * 1.1
+
+
+def mll_value_grad(kind, hypers, comp, vals, mean):
+    """(nlogprob, grad_nlogprob) of GP.optimize_hypers at log-hypers = [log amp2, log noise, log ls...] (GP:222-264),
+    INCLUDING the reference's length-scale 'gradient'  -amp2 * grad_corr[:, :, d] * comp[:, d, None]  (GP:258-259: the
+    exp(ls) factors cancel; it is not the derivative of the likelihood, but it is what L-BFGS-B is given)."""
+    amp2, noise, ls = np.exp(hypers[0]), np.exp(hypers[1]), np.exp(hypers[2:])
+    n, D = comp.shape
+    diffs = vals - mean
+    corr = kernel(kind, ls, comp)
+    grad_corr = grad_kernel(kind, ls, comp, comp)
+    covmat = amp2 * (corr + 1e-6 * np.eye(n)) + noise * np.eye(n)
+    chol, _ = jitter_chol(covmat)
+    solve = spla.cho_solve((chol, True), diffs)
+    f = -(-np.sum(np.log(np.diag(chol))) - 0.5 * np.dot(diffs, solve))
+    inv_cov = spla.cho_solve((chol, True), np.eye(n))
+    jac = np.outer(solve, solve) - inv_cov
+    g = np.zeros(D + 2)
+    g[0] = 0.5 * np.trace(np.dot(jac, corr + 1e-6 * np.eye(n))) * amp2
+    g[1] = 0.5 * np.trace(np.dot(jac, np.eye(n))) * noise
+    for d in range(D):
+        g[d + 2] = np.trace(np.dot(jac, -amp2 * grad_corr[:, :, d] * comp[:, d][:, None] / np.exp(ls[d]))) * np.exp(ls[d])
+    return f, -g
+
+
+def gp_optimize_hypers(kind, comp, vals):
+    """GP.optimize_hypers (GP:181-292): mean = mean(vals); L-BFGS-B over [log amp2, log noise, log ls] from
+    (std(vals), 1e-3, ones) within [-10, 10] x [-10, 10] x [-10, 5]^D.  Returns the hyper-sample tuple
+    (mean, noise, amp2, ls)."""
+    import scipy.optimize as spo
+    D = comp.shape[1]
+    mean = np.mean(vals)
+    x0 = np.zeros(D + 2)
+    x0[0], x0[1] = np.log(np.std(vals)), np.log(1e-3)
+    b = [(-10, 10), (-10, 10)] + [(-10, 5)] * D
+    res = spo.fmin_l_bfgs_b(lambda h: mll_value_grad(kind, h, comp, vals, mean)[0], x0,
+                            lambda h: mll_value_grad(kind, h, comp, vals, mean)[1], args=(), bounds=b)
+    h = res[0]
+    return mean, float(np.exp(h[1])), float(np.exp(h[0])), np.exp(h[2:])

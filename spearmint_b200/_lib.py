@@ -53,6 +53,9 @@ SIGNATURES = {
     "smk_ei_over_hypers_host_f32": ([_i, _i, _i, _i, _i] + [_p] * 9, _i),
     "smk_potrf_loglik_workspace_bytes": ([_i, _i], _sz),
     "smk_potrf_loglik_f64": ([_i, _i, _p, _p, _sz, _p, _i, _p], _i),
+    "smk_tc_guard_workspace_bytes": ([_i, _i], _sz),
+    "smk_tc_guard_f32": ([_i] * 4 + [_p] * 7 + [_sz, _p], _i),
+    "smk_ei_colsum": ([_i, _i, _p, _i, _p, _p], _i),
     "smk_tc_np": ([_i], _i),
     "smk_trtri_workspace_bytes": ([_i, _i], _sz),
     "smk_trtri_split_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
@@ -69,6 +72,8 @@ SIGNATURES = {
 }
 for _t in ("f32", "f64"):
     SIGNATURES.update({
+        "smk_sobol_generate_" + _t: ([_i, _ll, _ll, _p, _p, _p], _i),
+        "smk_mll_grad_terms_" + _t: ([_i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p], _i),
         "smk_cov_build_" + _t: ([_i] * 5 + [_p] * 6 + [_i, _p], _i),
         "smk_potrf_lower_batched_" + _t: ([_i, _i, _p, _p, _p, _p], _i),
         "smk_chol_solve_" + _t: ([_i] * 4 + [_p, _p, _p, _ll, _i, _p, _p, _p, _p, _p], _i),
@@ -76,7 +81,7 @@ for _t in ("f32", "f64"):
         "smk_loglik_finish_" + _t: ([_i, _i, _i, _p, _p, _p, _p], _i),
         "smk_predict_" + _t: ([_i] * 6 + [_p] * 10 + [_i, _p, _sz, _p], _i),
         "smk_cross_mean_" + _t: ([_i] * 7 + [_p] * 7 + [_i, _p], _i),
-        "smk_ei_sweep_" + _t: ([_i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p], _i),
+        "smk_ei_sweep_" + _t: ([_i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p], _i),
         "smk_topk_" + _t: ([_i, _i, _p, _p, _p, _p, _sz, _p], _i),
         "smk_ei_grad_terms_" + _t: ([_i] * 7 + [_p] * 8, _i),
     })

@@ -1,6 +1,7 @@
 """Compute backend of the chooser plugins: everything numerical that ``next()`` needs, on the GPU.
 
     loglik(kind, comp, vals)                      -> callable(mean, noise, amp2, ls) -> float   (float64, f2)
+    optimize_hypers(kind, comp, vals)             -> (mean, noise, amp2, ls)  ML-II, GP.optimize_hypers   (f3)
     grid_state(kind, hyper_samples, comp, pend, vals, normals, time_hs, durs_log) -> state
     ei_matrix(state, cand)                        -> (M, S) float64 numpy                        (OPT:331-341)
     top_mean_ei(state, cand, k)                   -> indices of the k largest mean-EI candidates, ascending (OPT:270, 294)
@@ -39,6 +40,15 @@ class DeviceBackend(object):
     # ---- f2
     def loglik(self, kind, comp, vals):
         return self.eng64.loglik(kind, comp, vals)
+
+    # ---- f3: ML-II hyper-parameters (gp.GP.optimize_hypers, GP:181-292)
+    def optimize_hypers(self, kind, comp, vals):
+        """-> (mean, noise, amp2, ls): L-BFGS-B on the host, likelihood value and gradient terms on the GPU in float64."""
+        from .gp import GP
+        g = GP(kind, engine=self.eng64)
+        g.real_init(comp.shape[1], vals)
+        g.optimize_hypers(comp, vals)
+        return g.mean, g.noise, g.amp2, g.ls
 
     # ---- grid pass
     def grid_state(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None,
@@ -79,7 +89,7 @@ class DeviceBackend(object):
         if not st.hs:
             ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
         elif st.preps is not None:
-            ei, ei_sum = eng.ei_prepared(st.preps, eng.to_dev(cand), want_matrix, None)
+            ei, ei_sum = eng.ei_prepared(st.preps, eng.to_dev(cand), want_matrix, None, cand_host=cand)
         else:
             comp, pend, vals, normals, durs_log = st.args
             try:                                     # chunked path: factors are (re)built per pass and may raise here
@@ -117,7 +127,10 @@ class DeviceBackend(object):
         parallel.allreduce_sum_(ei_sum)              # the single exchange of the path
         self._tail_fix(st, cand, None, ei_sum, M)    # deep-tail passes: exact float64 ranking of the short-list
         idx, _ = self.eng32.topk(ei_sum, M, k)       # argsort / argmax of the mean == of the sum
-        return idx.cpu().numpy().astype(int)
+        out = idx.cpu().numpy().astype(int)
+        if np.any(out < 0):                          # every score NaN: the reference's argmax would return index 0 of NaNs
+            raise FloatingPointError("EI is NaN for every candidate (non-finite hyper-parameters or inputs)")
+        return out
 
     # ---- f1
     def refine_context(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None,

@@ -6,7 +6,7 @@ The reference interleaves RNG use -- sample, fantasy normals (``npr.randn(P, F)`
 ... -- so the normals are drawn here in that same order and carried per sample; the EI passes themselves are then
 done for all samples in ONE batched GPU pass (``compute_ei`` math is identical to GPEIOptChooser's, GPEI:178-266).
 State pickle keys dims/ls/amp2/noise/mean, written on destruction like the reference (GPEI:66-84).
-``mcmc_iters=0`` (ML-II via gp.GP.optimize_hypers) is not provided.
+``mcmc_iters=0`` runs the ML-II branch: ``gp.GP.optimize_hypers`` (spearmint_b200/gp.py, GP:181-292) then EI under the optimum.
 """
 import os
 import pickle
@@ -92,7 +92,17 @@ class GPEIChooserB200(object):
         comp, cand, pend = grid[complete, :], grid[candidates, :], grid[pending, :]
         vals = values[complete]
         if self.mcmc_iters <= 0:
-            raise NotImplementedError("mcmc_iters=0 (gp.GP.optimize_hypers, ML-II) is not provided by GPEIChooserB200")
+            # ML-II branch (GPEI:156-176): optimise the hyper-parameters, EI under them, argmax
+            try:
+                self.optimize_hypers(comp, vals)
+            except Exception:                         # the reference's bare except: fall back to the initial values
+                self.ls = np.ones(self.D)
+                self.amp2 = np.std(vals)
+                self.noise = 1e-3
+            log("mean: %f  amp: %f  noise: %f  min_ls: %f  max_ls: %f"
+                % (self.mean, np.sqrt(self.amp2), self.noise, np.min(self.ls), np.max(self.ls)))
+            ei = self.compute_ei(comp, pend, cand, vals)
+            return int(candidates[int(np.argmax(ei))])
         P = pend.shape[0]
         self._ll = self.backend.loglik(self.covar, comp, vals)
         hs, normals = [], []
@@ -115,6 +125,10 @@ class GPEIChooserB200(object):
         st = self.backend.grid_state(self.covar, [(self.mean, self.noise, self.amp2, self.ls)], comp, pend, vals,
                                      normals)
         return self.backend.ei_matrix(st, cand)[:, 0]
+
+    def optimize_hypers(self, comp, vals):
+        """GPEI:348-361: a fresh gp.GP of the same kernel, ML-II from its own start values; the result replaces ours."""
+        self.mean, self.noise, self.amp2, self.ls = self.backend.optimize_hypers(self.covar, comp, vals)
 
     # ------------------------------------------------------------------ sampling (GPEI:268-346)
     def sample_hypers(self, comp, vals):

@@ -62,12 +62,15 @@ template <typename T>
 int cross_mean(int, int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, T*,
                int, cudaStream_t);
 template <typename T>
-int ei_sweep(int, int, int, const T*, const T*, int, const T*, const T*, double*, double*, cudaStream_t);
+int ei_sweep(int, int, int, const T*, const T*, int, const T*, const T*, double*, double*, unsigned long long*, cudaStream_t);
+int ei_colsum(int, int, const double*, int, double*, cudaStream_t);
 template <typename T>
 int topk(int, int, const T*, int*, T*, void*, size_t, cudaStream_t);
 template <typename T>
 int ei_grad_terms(int, int, int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, T*,
                   cudaStream_t);
+template <typename T>
+int mll_grad_terms(int, int, int, int, const T*, const T*, const T*, int, const T*, int, double*, cudaStream_t);
 size_t topk_workspace_bytes(int, int);
 int tc_np(int);
 size_t trtri_workspace_bytes(int, int);
@@ -87,6 +90,11 @@ int predict_tc(int, int, int, int, int, int, const float*, const float*, const f
                int, const float*, float*, cudaStream_t);
 size_t predict_workspace_bytes_any(int, int);
 size_t potrf_ll_workspace_bytes(int, int);
+template <typename T>
+int sobol_generate(int, long, long, const uint32_t*, T*, cudaStream_t);
+size_t tc_guard_workspace_bytes(int, int);
+int tc_guard(int, int, int, int, const float*, const float*, const float*, const float*, const float*, float*, void*, size_t,
+             cudaStream_t);
 int potrf_ll_f64(int, int, double*, double*, int*, int, cudaStream_t);
 
 }  // namespace smk
@@ -208,6 +216,17 @@ int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* 
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream) {
   return linv_alpha(N, Np, S, linv_hi, linv_lo, y, mean, alpha, ld_alpha, tmp, ST(stream));
 }
+int smk_sobol_generate_f32(int D, long long n, long long skip, const uint32_t* V, float* out, void* stream) {
+  return sobol_generate<float>(D, (long)n, (long)skip, V, out, ST(stream));
+}
+int smk_sobol_generate_f64(int D, long long n, long long skip, const uint32_t* V, double* out, void* stream) {
+  return sobol_generate<double>(D, (long)n, (long)skip, V, out, ST(stream));
+}
+size_t smk_tc_guard_workspace_bytes(int Np, int S) { return tc_guard_workspace_bytes(Np, S); }
+int smk_tc_guard_f32(int N, int Npad, int Np, int S, const float* L, const float* linv_hi, const float* linv_lo,
+                     const float* amp2, const float* noise, float* g, void* workspace, size_t workspace_bytes, void* stream) {
+  return tc_guard(N, Npad, Np, S, L, linv_hi, linv_lo, amp2, noise, g, workspace, workspace_bytes, ST(stream));
+}
 int smk_debug_kxt_tc_timeline(long long* out, int n) { return kxt_tc_timeline(out, n); }
 size_t smk_kxt_pack_workspace_bytes(int Np, int M, int S) { return kxt_pack_workspace_bytes(Np, M, S); }
 int smk_kxt_pack_f16(int impl, int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
@@ -244,12 +263,15 @@ int smk_cross_mean_f64(int kind, int N, int Npad, int M, int D, int S, int F, co
 }
 
 int smk_ei_sweep_f32(int M, int S, int F, const float* mu, const float* var, int ldm, const float* best,
-                     const float* log_time, double* ei, double* ei_sum, void* stream) {
-  return ei_sweep<float>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ST(stream));
+                     const float* log_time, double* ei, double* ei_sum, unsigned long long* ei_max, void* stream) {
+  return ei_sweep<float>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ei_max, ST(stream));
 }
 int smk_ei_sweep_f64(int M, int S, int F, const double* mu, const double* var, int ldm, const double* best,
-                     const double* log_time, double* ei, double* ei_sum, void* stream) {
-  return ei_sweep<double>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ST(stream));
+                     const double* log_time, double* ei, double* ei_sum, unsigned long long* ei_max, void* stream) {
+  return ei_sweep<double>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ei_max, ST(stream));
+}
+int smk_ei_colsum(int M, int S, const double* ei, int ldm, double* ei_sum, void* stream) {
+  return ei_colsum(M, S, ei, ldm, ei_sum, ST(stream));
 }
 
 size_t smk_topk_workspace_bytes(int M, int k) { return topk_workspace_bytes(M, k); }
@@ -273,6 +295,15 @@ int smk_ei_grad_terms_f64(int kind, int N, int Npad, int D, int S, int Q, int F,
                           double* out, void* stream) {
   if (kind == SMK_SE) return -1;
   return ei_grad_terms<double>(kind, N, Npad, D, S, Q, F, X, xq, inv_ls, amp2, alpha, gamma, out, ST(stream));
+}
+
+int smk_mll_grad_terms_f32(int kind, int N, int D, int S, const float* X, const float* inv_ls, const float* alpha, int lda,
+                           const float* Kinv, int ldk, double* out, void* stream) {
+  return mll_grad_terms<float>(kind, N, D, S, X, inv_ls, alpha, lda, Kinv, ldk, out, ST(stream));
+}
+int smk_mll_grad_terms_f64(int kind, int N, int D, int S, const double* X, const double* inv_ls, const double* alpha, int lda,
+                           const double* Kinv, int ldk, double* out, void* stream) {
+  return mll_grad_terms<double>(kind, N, D, S, X, inv_ls, alpha, lda, Kinv, ldk, out, ST(stream));
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -359,7 +390,7 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   if ((rc = smk_predict_tc_f32(kind, N, Np, M, D, S, dX, dC, dil, da, dm, lh16, ll16, lexp, alpha, Npad, mv,
                                mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, st)))
     return rc;
-  if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, st))) return rc;
+  if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, nullptr, st))) return rc;
   std::vector<double> hout((size_t)S * ldm);
   std::vector<int> hinfo(S);
   cudaMemcpyAsync(hout.data(), ei, hout.size() * sizeof(double), cudaMemcpyDeviceToHost, st);

@@ -214,6 +214,14 @@ __device__ __forceinline__ T kernel_of_r2(int kind, T r2) {
   return (T(1) + a + T(5.0 / 3.0) * r2) * smk_exp(-a);
 }
 
+// round-to-nearest tf32 (10 explicit mantissa bits); x - tf32_rn(x) is exact in float32 and symmetric around zero, unlike the
+// truncating split (x & 0xffffe000) whose dropped lo*lo products are all of one sign
+__device__ __forceinline__ float tf32_rn(float x) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // launch bookkeeping (api.cu)
 void count_launch(int n = 1);
 long long launch_count();

@@ -1,43 +1,119 @@
-// diag.cuh -- factor one NB x NB diagonal block of the blocked Cholesky on ONE SM and invert its factor.
+// diag.cuh -- the serial spine of every blocked Cholesky in the library, taken off the critical path as far as it goes.
 //
-// This kernel is the serial spine of every factorisation in the library (reference: spla.cholesky at OPT:540, 567, 585
-// and inside every slice-sampler log-probability OPT:637, 659, 690): Npad / NB launches per matrix, strictly one after
-// the other, so what matters is its latency.  Round 1 used block-wide barriers around every column of every 32 x 32
-// piece (155 us for a 128 x 128 float block).  Here:
-//   * the block lives in shared memory as 32 x 32 tiles (row stride 33: conflict-free by row and by column);
-//   * a 32 x 32 diagonal piece is factored by ONE warp, warp-synchronously: lane = row, the row sits in registers, a
-//     column step is one shuffle (pivot), one rsqrt, a 32-entry broadcast buffer and 31 - j fused multiply-adds --
-//     no block barrier inside the piece;
-//   * rows below the piece are solved by substitution with one thread per row (registers), not via the inverse;
-//   * the rank-32 update of what is left of the block is register-tiled 4 x 4 over all 256 threads;
-//   * W = L^-1 is assembled at the end: the four 32 x 32 diagonal inverses concurrently (one warp each, lane = column,
-//     column in registers), then the off-diagonal tiles by block distance.
+// Reference: spla.cholesky at OPT:540, 567, 585 and inside every slice-sampler log-probability OPT:637, 659, 690.  A
+// blocked factorisation runs Npad / NB diagonal-block steps strictly one after the other, so the latency of one step --
+// not its flops -- bounds the factorisation of a single matrix.  Round 1 did everything a step needs in one kernel with
+// block-wide barriers around every column of every 32 x 32 piece (155 us per 128 x 128 float block, 62 us per 64 x 64
+// double block).  A clock64() timeline of the first rewrite (tools/microbench/diag_bench.cu, profiles/r02_diag_timeline.md)
+// showed where a step really goes -- 33 % assembling the off-diagonal tiles of W = L^-1, 23 % a latency-bound load loop,
+// 20 % the four 32 x 32 factorisations, 12 % the rank-32 updates -- hence this split:
+//
+//   diag_factor_block   (one CTA per matrix, ON the spine)  load (8 loads in flight per thread) -> for each 32-piece:
+//                       warp-synchronous Cholesky of the piece (lane = row, row in registers), substitution for the rows
+//                       below (thread = row), rank-32 update of the rest (float64: mma.sync.m8n8k4.f64 tiles, float32:
+//                       4 x 4 register tiles) -> the four 32 x 32 diagonal inverses (one warp each).  Writes L and the
+//                       compact  wd[4][32][32].
+//   panel_sub_block     (many CTAs, 32 rows each)  L_Ij = A_Ij L_jj^-T by BLOCK substitution with the diagonal inverses:
+//                       X_p = (A_p - sum_{q<p} X_q L_pq^T) W_pp^T  -- the full inverse is not needed for the panel.
+//   winv_assemble_block (one CTA per block, OFF the spine, after the factorisation, all blocks at once)  full W_jj from
+//                       L_jj and wd for the consumers that multiply by it (triangular inverse, multi-RHS solves, SIMT
+//                       predict).
+// Shared-memory tiles are 32 x 32 with row stride LDT = 36 (float64: conflict-free 8-byte DMMA fragment loads in both
+// orientations) or 33 (float32: conflict-free by row and by column).
 #pragma once
 #include "common.cuh"
 
 namespace smk {
 
+// optional phase timeline (tools/microbench/diag_bench.cu defines SMK_DIAG_TIMELINE): clock64() stamps of thread 0
+#ifdef SMK_DIAG_TIMELINE
+__device__ long long g_diag_tl[64];
+#define DIAG_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_diag_tl[i] = clock64(); } while (0)
+#else
+#define DIAG_STAMP(i) do { } while (0)
+#endif
+
 template <typename T> __device__ __forceinline__ T smk_rsqrt(T x);
 template <> __device__ __forceinline__ float smk_rsqrt<float>(float x) { return 1.0f / sqrtf(x); }
 template <> __device__ __forceinline__ double smk_rsqrt<double>(double x) { return rsqrt(x); }
 
+template <typename T> struct TileLd { static constexpr int v = 33; };
+template <> struct TileLd<double> { static constexpr int v = 36; };
+
 template <typename T, int NB>
 struct DiagSmem {
-  static constexpr int SB = 32, LDT = 33, NP = NB / SB, NT = NP * (NP + 1) / 2;
+  static constexpr int SB = 32, LDT = TileLd<T>::v, NP = NB / SB, NT = NP * (NP + 1) / 2;
   static constexpr int TILE = SB * LDT;
-  // a tiles | w tiles | broadcast column [32] | inverse pivots [NB]
-  static constexpr size_t bytes = sizeof(T) * ((size_t)2 * NT * TILE + 32 + NB);
-  static __device__ __forceinline__ int tile(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * TILE; }
+  // a tiles (lower block triangle) | NP diagonal inverse tiles | broadcast column [32] | inverse pivots [NB]
+  static constexpr size_t bytes = sizeof(T) * ((size_t)(NT + NP) * TILE + 32 + NB);
+  static __host__ __device__ __forceinline__ int tile(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * TILE; }
 };
 
-// Lower Cholesky of the 32 x 32 piece at `a` (tile, row stride 33) by the calling warp; lane = row.
-// `col` is a 32-entry broadcast buffer, ipv receives 1 / L_jj.  Returns the first bad pivot (or -1) in `bad`.
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------ 32 x 32 block product
+// acc (+)= A * B^T for one 32 x 32 output block, K = 32, all 256 threads.  A(r, k) at A[r * sar + k * sak], B(c, k) at
+// B[c * sbc + k * sbk] (shared memory).  The accumulator fragment stays in registers across calls:
+//   double: warp w owns the 8 x 8 tiles 2w and 2w+1 (tile t: rows (t / 4) * 8.., columns (t % 4) * 8..), DMMA layout;
+//   float : thread (ty = tid / 16, tx = tid % 16) owns rows 2ty, 2ty+1 x columns 2tx, 2tx+1.
+template <typename T> struct BlkAcc;
+template <> struct BlkAcc<double> { double c[2][2]; };
+template <> struct BlkAcc<float> { float c[2][2]; };
+
+template <typename T> __device__ __forceinline__ void blk_zero(BlkAcc<T>& a) {
+  a.c[0][0] = a.c[0][1] = a.c[1][0] = a.c[1][1] = T(0);
+}
+__device__ __forceinline__ void blk_mma(BlkAcc<double>& acc, const double* A, int sar, int sak, const double* B, int sbc,
+                                        int sbk) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = 2 * warp + u, r0 = (t >> 2) * 8, c0 = (t & 3) * 8;
+    const double* ap = A + (r0 + gq) * sar + t4 * sak;
+    const double* bp = B + (c0 + gq) * sbc + t4 * sbk;
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) dmma_884(acc.c[u], ap[k * sak], bp[k * sbk]);
+  }
+}
+__device__ __forceinline__ void blk_mma(BlkAcc<float>& acc, const float* A, int sar, int sak, const float* B, int sbc,
+                                        int sbk) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const float* a0 = A + (2 * ty) * sar;
+  const float* b0 = B + (2 * tx) * sbc;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) {
+    const float x0 = a0[k * sak], x1 = a0[sar + k * sak], y0 = b0[k * sbk], y1 = b0[sbc + k * sbk];
+    acc.c[0][0] = fmaf(x0, y0, acc.c[0][0]); acc.c[0][1] = fmaf(x0, y1, acc.c[0][1]);
+    acc.c[1][0] = fmaf(x1, y0, acc.c[1][0]); acc.c[1][1] = fmaf(x1, y1, acc.c[1][1]);
+  }
+}
+// element (i, j) of the calling thread's fragment -> (row, column) inside the 32 x 32 block
+__device__ __forceinline__ void blk_coord(const BlkAcc<double>&, int i, int j, int& r, int& c) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = 2 * warp + i;
+  r = (t >> 2) * 8 + (lane >> 2);
+  c = (t & 3) * 8 + (lane & 3) * 2 + j;
+}
+__device__ __forceinline__ void blk_coord(const BlkAcc<float>&, int i, int j, int& r, int& c) {
+  r = 2 * (threadIdx.x >> 4) + i;
+  c = 2 * (threadIdx.x & 15) + j;
+}
+
+// ------------------------------------------------------------------------------------------------ 32 x 32 pieces
+// Lower Cholesky of the 32 x 32 piece at `a` (tile, row stride LDT) by the calling warp; lane = row.
+// `col` is a 32-entry broadcast buffer, ipv receives 1 / L_jj.  `bad`: first non-positive pivot (or -1).
 template <typename T>
 __device__ __forceinline__ void warp_chol32(T* a, T* col, T* ipv, int lane, int& bad) {
-  constexpr int LDT = 33;
+  constexpr int LDT = TileLd<T>::v;
+  (void)col;
   T r[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) r[k] = (k <= lane) ? a[lane * LDT + k] : T(0);
+  // Column step j: pivot from lane j, every lane scales its entry, then row k of the update needs l of lane k -- all by
+  // register shuffles: no shared-memory round trip and no warp barrier inside the piece, so the compiler overlaps the
+  // update of step j with the pivot chain (shuffle -> rsqrt -> multiply -> shuffle -> fma) of step j + 1.
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     T d = __shfl_sync(0xffffffffu, r[j], j);
@@ -46,11 +122,11 @@ __device__ __forceinline__ void warp_chol32(T* a, T* col, T* ipv, int lane, int&
     const T l = r[j] * ip;                       // lane j: d / sqrt(d) = sqrt(d)
     if (lane >= j) r[j] = l;
     if (lane == j) ipv[j] = ip;
-    col[lane] = l;
-    __syncwarp();
 #pragma unroll
-    for (int k = j + 1; k < 32; ++k) r[k] = fma(-l, col[k], r[k]);   // meaningful for j < k <= lane
-    __syncwarp();
+    for (int k = j + 1; k < 32; ++k) {
+      const T lk = __shfl_sync(0xffffffffu, l, k);
+      r[k] = fma(-l, lk, r[k]);                  // meaningful for j < k <= lane
+    }
   }
 #pragma unroll
   for (int k = 0; k < 32; ++k)
@@ -60,7 +136,7 @@ __device__ __forceinline__ void warp_chol32(T* a, T* col, T* ipv, int lane, int&
 // W = L^-1 of a 32 x 32 lower-triangular tile by the calling warp; lane = column c, the column lives in registers.
 template <typename T>
 __device__ __forceinline__ void warp_trinv32(const T* l, const T* ipv, T* w, int lane) {
-  constexpr int LDT = 33;
+  constexpr int LDT = TileLd<T>::v;
   T x[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -79,25 +155,106 @@ __device__ __forceinline__ void warp_trinv32(const T* l, const T* ipv, T* w, int
   for (int i = 0; i < 32; ++i) w[i * LDT + lane] = x[i];
 }
 
-// A: [..][ld] matrix of this sample, block (jb, jb) is factored in place (lower triangle; the strict upper triangle of
-// the block is left untouched); Wb: NB x NB row-major, receives L_jj^-1 (zeros above the diagonal).
+// rank-32 update of the lower triangle left of piece p:  C[r][c] -= X[r] . X[c]  for r >= c (rows relative to the first
+// remaining row; X = tiles (bi, p), C = tiles (bi, bj)).
+template <int NB>
+__device__ __forceinline__ void diag_update(double* a, int p) {
+  using DS = DiagSmem<double, NB>;
+  constexpr int LDT = DS::LDT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+  const int nt8 = (NB - (p + 1) * 32) / 8;                // 8 x 8 tiles per side
+  for (int e = warp; e < nt8 * (nt8 + 1) / 2; e += 8) {   // lower tile triangle, one DMMA tile per warp and round
+    int tr = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+    while (tr * (tr + 1) / 2 > e) --tr;
+    while ((tr + 1) * (tr + 2) / 2 <= e) ++tr;
+    const int tc = e - tr * (tr + 1) / 2;
+    const int r0 = tr * 8, c0 = tc * 8;
+    const double* xr = a + DS::tile(p + 1 + (r0 >> 5), p) + ((r0 & 31) + gq) * LDT + t4;
+    const double* xc = a + DS::tile(p + 1 + (c0 >> 5), p) + ((c0 & 31) + gq) * LDT + t4;
+    double c[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) dmma_884(c, xr[k], xc[k]);
+    double* ct = a + DS::tile(p + 1 + (r0 >> 5), p + 1 + (c0 >> 5)) + ((r0 & 31) + gq) * LDT + (c0 & 31) + t4 * 2;
+    ct[0] -= c[0];
+    ct[1] -= c[1];                                        // entries above the diagonal of a diagonal tile are never read
+  }
+}
+template <int NB>
+__device__ __forceinline__ void diag_update(float* a, int p) {
+  // A thread owns the 4 x 4 elements (gr + i nt, gc + j nt): consecutive lanes read consecutive rows of X (conflict-free,
+  // stride 33) and share the other operand (broadcast).  i > j is always below the diagonal, i == j iff gr >= gc.
+  using DS = DiagSmem<float, NB>;
+  constexpr int LDT = DS::LDT, SB = 32;
+  const int rows = NB - (p + 1) * SB, nt = rows / 4;
+  for (int e = threadIdx.x; e < nt * nt; e += 256) {
+    const int gr = e / nt, gc = e % nt;
+    const bool dg = gr >= gc;
+    const float* xr[4];
+    const float* xc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = gr + i * nt, c = gc + i * nt;
+      xr[i] = a + DS::tile(p + 1 + (r >> 5), p) + (r & 31) * LDT;
+      xc[i] = a + DS::tile(p + 1 + (c >> 5), p) + (c & 31) * LDT;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < SB; ++k) {
+      float xa[4], xb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xa[i] = xr[i][k]; xb[i] = xc[i][k]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) acc[i][j] = fmaf(xa[i], xb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        if (i == j && !dg) continue;
+        const int r = gr + i * nt, c = gc + j * nt;
+        a[DS::tile(p + 1 + (r >> 5), p + 1 + (c >> 5)) + (r & 31) * LDT + (c & 31)] -= acc[i][j];
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the spine kernel body
+// Ab: block (jb, jb) of this sample's matrix (row stride ld), factored in place (lower triangle; the strict upper triangle
+// is left untouched).  wd: [NB/32][32][32] receives the inverses of the 32 x 32 diagonal pieces of L_jj.
 // info (may be NULL): 1-based index of the first non-positive pivot, written once.
 template <typename T, int NB>
-__device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ Wb, int* info, int info_base, T* sm) {
+__device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ wd, int* info, int info_base, T* sm) {
   using DS = DiagSmem<T, NB>;
-  constexpr int SB = 32, LDT = 33, NP = DS::NP, TILE = DS::TILE;
+  constexpr int SB = 32, LDT = DS::LDT, NP = DS::NP, TILE = DS::TILE;
   T* a = sm;
-  T* w = a + DS::NT * TILE;
-  T* col = w + DS::NT * TILE;
+  T* w = a + DS::NT * TILE;                 // NP diagonal inverse tiles
+  T* col = w + NP * TILE;
   T* ipv = col + 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- load the lower triangle as tiles (rows of 32 contiguous elements per warp: coalesced)
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, k = e % NB;
-    if ((k >> 5) <= (i >> 5)) a[DS::tile(i >> 5, k >> 5) + (i & 31) * LDT + (k & 31)] = (k <= i) ? Ab[(long)i * ld + k] : T(0);
-  }
+  DIAG_STAMP(0);
+  // ---- load the lower block triangle tile by tile: a warp reads 32 contiguous elements of a row, 4 loads in flight
+  for (int bi = 0; bi < NP; ++bi)
+    for (int bj = 0; bj <= bi; ++bj) {
+      T v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * 256, i = e >> 5, k = e & 31;
+        v[q] = (bj < bi || k <= i) ? Ab[(long)(bi * SB + i) * ld + bj * SB + k] : T(0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * 256;
+        a[DS::tile(bi, bj) + (e >> 5) * LDT + (e & 31)] = v[q];
+      }
+    }
   __syncthreads();
+  DIAG_STAMP(1);
 
   for (int p = 0; p < NP; ++p) {
     // (a) diagonal piece
@@ -107,6 +264,7 @@ __device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ Wb
       if (bad >= 0 && lane == 0 && info && *info == 0) *info = info_base + p * SB + bad + 1;
     }
     __syncthreads();
+    DIAG_STAMP(2 + 4 * p);
     const int rows = NB - (p + 1) * SB;
     if (rows == 0) break;
     // (b) rows below: X L_pp^T = A_sub by substitution, one thread per row (x_k needs x_0..x_{k-1}: registers)
@@ -135,94 +293,165 @@ __device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ Wb
       for (int k = 0; k < 32; ++k) ar[k] = x[k];
     }
     __syncthreads();
-    // (c) rank-32 update of the remaining lower triangle: C[r][c] -= X[r] . X[c] for r >= c.  A thread owns the 4 x 4
-    //     elements (gr + i nt, gc + j nt): consecutive lanes read consecutive rows of X (conflict-free, stride 33) and
-    //     share the other operand (broadcast).  i > j is always below the diagonal, i == j iff gr >= gc, i < j never.
-    const int nt = rows / 4;
-    for (int e = tid; e < nt * nt; e += 256) {
-      const int gr = e / nt, gc = e % nt;
-      const bool dg = gr >= gc;
-      const T* xr[4];
-      const T* xc[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = gr + i * nt, c = gc + i * nt;
-        xr[i] = a + DS::tile(p + 1 + (r >> 5), p) + (r & 31) * LDT;
-        xc[i] = a + DS::tile(p + 1 + (c >> 5), p) + (c & 31) * LDT;
-      }
-      T acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-#pragma unroll 8
-      for (int k = 0; k < SB; ++k) {
-        T xa[4], xb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { xa[i] = xr[i][k]; xb[i] = xc[i][k]; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j <= i; ++j) acc[i][j] = fma(xa[i], xb[j], acc[i][j]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-          if (i == j && !dg) continue;
-          const int r = gr + i * nt, c = gc + j * nt;
-          a[DS::tile(p + 1 + (r >> 5), p + 1 + (c >> 5)) + (r & 31) * LDT + (c & 31)] -= acc[i][j];
-        }
-    }
+    DIAG_STAMP(3 + 4 * p);
+    // (c) rank-32 update of the remaining lower triangle
+    diag_update<NB>(a, p);
     __syncthreads();
+    DIAG_STAMP(4 + 4 * p);
   }
+  DIAG_STAMP(20);
 
-  // ---- W = L^-1: diagonal tiles (one warp each), then off-diagonal tiles by block distance
-  if (warp < NP) warp_trinv32<T>(a + DS::tile(warp, warp), ipv + warp * SB, w + DS::tile(warp, warp), lane);
+  // ---- inverses of the diagonal pieces, one warp each
+  if (warp < NP) warp_trinv32<T>(a + DS::tile(warp, warp), ipv + warp * SB, w + warp * TILE, lane);
   __syncthreads();
-  for (int d = 1; d < NP; ++d) {
-    // W_ij = -W_ii * (sum_{k=j}^{i-1} L_ik W_kj), i = j + d.  T_ij goes through the (free) strictly-lower tile of w.
-    const int npair = NP - d;
-    for (int e = tid; e < npair * SB * SB; e += 256) {
-      const int pr = e / (SB * SB), rr = (e / SB) % SB, cc = e % SB;
-      const int j = pr, i = pr + d;
-      T acc = T(0);
-      for (int kb = j; kb < i; ++kb) {
-        const T* lrow = a + DS::tile(i, kb) + rr * LDT;
-        const T* wk = w + DS::tile(kb, j) + cc;
-#pragma unroll 8
-        for (int m = 0; m < SB; ++m) acc = fma(lrow[m], wk[m * LDT], acc);
+  DIAG_STAMP(21);
+
+  // ---- store L (lower triangle) tile by tile and the compact diagonal inverses
+  for (int bi = 0; bi < NP; ++bi)
+    for (int bj = 0; bj <= bi; ++bj)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * 256, i = e >> 5, k = e & 31;
+        if (bj < bi || k <= i) Ab[(long)(bi * SB + i) * ld + bj * SB + k] = a[DS::tile(bi, bj) + i * LDT + k];
       }
-      w[DS::tile(i, j) + rr * LDT + cc] = acc;
-    }
+  for (int e = tid; e < NP * SB * SB; e += 256) {
+    const int pp = e >> 10, i = (e >> 5) & 31, k = e & 31;
+    wd[e] = (k <= i) ? w[pp * TILE + i * LDT + k] : T(0);
+  }
+  DIAG_STAMP(22);
+}
+
+// ------------------------------------------------------------------------------------------------ panel by block substitution
+// 32 rows of the panel below block (jb, jb):  X = A L_jj^-T  as  X_p = (A_p - sum_{q<p} X_q L_pq^T) W_pp^T, p = 0..NP-1.
+// Ap: first of the 32 rows (row stride ld), columns of block column jb;  Ljj: the factored diagonal block (row stride ld);
+// wd: its diagonal inverses.  Result overwrites Ap; optional tf32 (hi, lo) copies for the tcgen05 update (float only).
+template <typename T, int NB>
+struct PanelSmem {
+  static constexpr int SB = 32, LDT = TileLd<T>::v, NP = NB / SB, TILE = SB * LDT;
+  // L off-diagonal tiles (NP (NP-1) / 2) | NP diagonal inverses | NP row tiles of the panel | 1 scratch tile
+  static constexpr int NL = NP * (NP - 1) / 2;
+  static constexpr size_t bytes = sizeof(T) * (size_t)(NL + NP + NP + 1) * TILE;
+};
+
+template <typename T, int NB>
+__device__ void panel_sub_block(T* __restrict__ Ap, int ld, const T* __restrict__ Ljj, const T* __restrict__ wd,
+                                T* __restrict__ hi, T* __restrict__ lo, T* sm) {
+  using PS = PanelSmem<T, NB>;
+  constexpr int SB = 32, LDT = PS::LDT, NP = PS::NP, TILE = PS::TILE;
+  T* lt = sm;                               // off-diagonal tile (pi, pj), pj < pi, at index pi (pi - 1) / 2 + pj
+  T* wt = lt + PS::NL * TILE;
+  T* xt = wt + NP * TILE;                   // panel rows: tile q = columns 32 q .. 32 q + 31
+  T* tt = xt + NP * TILE;                   // scratch: A_p - sum
+  const int tid = threadIdx.x;
+  // ---- loads (coalesced 32-element row segments)
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, k = e % NB, bi = i >> 5, bk = k >> 5;
+    if (bk < bi) lt[(bi * (bi - 1) / 2 + bk) * TILE + (i & 31) * LDT + (k & 31)] = Ljj[(long)i * ld + k];
+  }
+  for (int e = tid; e < NP * SB * SB; e += 256) wt[(e / (SB * SB)) * TILE + ((e / SB) % SB) * LDT + (e % SB)] = wd[e];
+  for (int e = tid; e < SB * NB; e += 256) {
+    const int i = e / NB, k = e % NB;
+    xt[(k >> 5) * TILE + i * LDT + (k & 31)] = Ap[(long)i * ld + k];
+  }
+  __syncthreads();
+  BlkAcc<T> acc;
+  for (int p = 0; p < NP; ++p) {
+    blk_zero(acc);
+    for (int q = 0; q < p; ++q)               // sum_q X_q L_pq^T : A(r, k) = X_q[r][k], B(c, k) = L_pq[c][k]
+      blk_mma(acc, xt + q * TILE, LDT, 1, lt + (p * (p - 1) / 2 + q) * TILE, LDT, 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        int r, c;
+        blk_coord(acc, i, j, r, c);
+        tt[r * LDT + c] = xt[p * TILE + r * LDT + c] - acc.c[i][j];
+      }
     __syncthreads();
-    // in-place multiply by -W_ii: column cc of T_ij is read fully before it is overwritten (thread = (pair, column))
-    for (int e = tid; e < npair * SB; e += 256) {
-      const int pr = e / SB, cc = e % SB;
-      const int j = pr, i = pr + d;
-      T* tcol = w + DS::tile(i, j) + cc;
-      const T* wii = w + DS::tile(i, i);
-      T tv[32];
+    blk_zero(acc);
+    blk_mma(acc, tt, LDT, 1, wt + p * TILE, LDT, 1);      // X_p = T W_pp^T : B(c, k) = W_pp[c][k]
+    __syncthreads();                                       // everybody is done reading tt (and X_p's old values)
 #pragma unroll
-      for (int m = 0; m < 32; ++m) tv[m] = tcol[m * LDT];
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        T acc = T(0);
-#pragma unroll
-        for (int m = 0; m <= rr; ++m) acc = fma(wii[rr * LDT + m], tv[m], acc);
-        tcol[rr * LDT] = -acc;
+      for (int j = 0; j < 2; ++j) {
+        int r, c;
+        blk_coord(acc, i, j, r, c);
+        xt[p * TILE + r * LDT + c] = acc.c[i][j];
       }
-    }
     __syncthreads();
   }
+  for (int e = tid; e < SB * NB; e += 256) {
+    const int i = e / NB, k = e % NB;
+    const T x = xt[(k >> 5) * TILE + i * LDT + (k & 31)];
+    Ap[(long)i * ld + k] = x;
+    if constexpr (sizeof(T) == 4) {
+      if (hi != nullptr) {                   // tf32 (hi, lo) copy of the finished panel: round-to-nearest split
+        const float h = tf32_rn(x);
+        hi[(long)i * ld + k] = h;
+        lo[(long)i * ld + k] = x - h;
+      }
+    }
+  }
+}
 
-  // ---- store L (lower triangle only) and W (full block, zeros above the diagonal)
+// ------------------------------------------------------------------------------------------------ full inverse, off the spine
+// W_jj = L_jj^-1 (NB x NB row-major, zeros above the diagonal) from L_jj and the diagonal inverses:
+//   W_ij = -W_ii (sum_{k=j}^{i-1} L_ik W_kj)   by block distance d = i - j = 1, 2, ...
+template <typename T, int NB>
+struct WinvSmem {
+  static constexpr int SB = 32, LDT = TileLd<T>::v, NP = NB / SB, NT = NP * (NP + 1) / 2, TILE = SB * LDT;
+  static constexpr size_t bytes = sizeof(T) * (size_t)(2 * NT + 1) * TILE;     // L tiles | W tiles | scratch
+};
+template <typename T, int NB>
+__device__ void winv_assemble_block(const T* __restrict__ Ljj, int ld, const T* wd, T* Wb, T* sm) {   // wd may alias Wb
+  using WS = WinvSmem<T, NB>;
+  using DS = DiagSmem<T, NB>;
+  constexpr int SB = 32, LDT = WS::LDT, NP = WS::NP, TILE = WS::TILE;
+  T* a = sm;
+  T* w = a + WS::NT * TILE;
+  T* tt = w + WS::NT * TILE;
+  const int tid = threadIdx.x;
   for (int e = tid; e < NB * NB; e += 256) {
     const int i = e / NB, k = e % NB;
-    const bool low = (k >> 5) <= (i >> 5);
-    const int o = low ? DS::tile(i >> 5, k >> 5) + (i & 31) * LDT + (k & 31) : 0;
-    if (k <= i) Ab[(long)i * ld + k] = a[o];
-    Wb[e] = (k <= i) ? w[o] : T(0);
+    if ((k >> 5) < (i >> 5)) a[DS::tile(i >> 5, k >> 5) + (i & 31) * LDT + (k & 31)] = Ljj[(long)i * ld + k];
+  }
+  for (int e = tid; e < NP * SB * SB; e += 256) {
+    const int pp = e / (SB * SB);
+    w[DS::tile(pp, pp) + ((e / SB) % SB) * LDT + (e % SB)] = wd[e];
+  }
+  __syncthreads();
+  BlkAcc<T> acc;
+  for (int d = 1; d < NP; ++d)
+    for (int j = 0; j + d < NP; ++j) {
+      const int i = j + d;
+      blk_zero(acc);
+      for (int kb = j; kb < i; ++kb)          // T = sum L_ik W_kj : A(r, m) = L_ik[r][m], B(c, m) = W_kj[m][c]
+        blk_mma(acc, a + DS::tile(i, kb), LDT, 1, w + DS::tile(kb, j), 1, LDT);
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          int r, c;
+          blk_coord(acc, x, y, r, c);
+          tt[r * LDT + c] = acc.c[x][y];
+        }
+      __syncthreads();
+      blk_zero(acc);
+      blk_mma(acc, w + DS::tile(i, i), LDT, 1, tt, 1, LDT);      // W_ii T : B(c, m) = T[m][c]
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          int r, c;
+          blk_coord(acc, x, y, r, c);
+          w[DS::tile(i, j) + r * LDT + c] = -acc.c[x][y];
+        }
+      __syncthreads();
+    }
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, k = e % NB;
+    Wb[e] = (k <= i) ? w[DS::tile(i >> 5, k >> 5) + (i & 31) * LDT + (k & 31)] : T(0);
   }
 }
 

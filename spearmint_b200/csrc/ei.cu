@@ -22,6 +22,43 @@ __device__ __forceinline__ double ei_one(double best, double m, double v) {
   return s * (u * cdf + pdf);
 }
 
+
+// EI of candidate j under sample s (mean over the F fantasies, optional division by the predicted duration)
+template <typename T>
+__device__ __forceinline__ double ei_cand(int F, const T* mu, const T* var, int ldm, const T* best, const T* log_time, int s,
+                                          int j) {
+  const double v = (double)var[(long)s * ldm + j];
+  const T* mrow = mu + (long)s * F * ldm + j;
+  const T* brow = best + (long)s * F;
+  double acc = 0.0;
+  for (int f = 0; f < F; ++f) acc += ei_one((double)brow[f], (double)mrow[(long)f * ldm], v);
+  double e = (F > 1) ? acc / (double)F : acc;
+  if (log_time) e /= exp((double)log_time[(long)s * ldm + j]);
+  return e;
+}
+
+// Variant of the sweep that also leaves max_j EI[s][j] in ei_max[s] (the accuracy guard of the engine compares it with
+// the error bound of the explicit-inverse path).  One warp-level + one atomic reduction per (block, sample).
+template <typename T>
+__device__ __forceinline__ void ei_sweep_with_max(int M, int S, int F, const T* mu, const T* var, int ldm, const T* best,
+                                                  const T* log_time, double* ei, double* ei_sum, unsigned long long* ei_max,
+                                                  int j) {
+  double total = 0.0;
+  for (int s = 0; s < S; ++s) {
+    double e = 0.0;
+    if (j < M) {
+      e = ei_cand<T>(F, mu, var, ldm, best, log_time, s, j);
+      if (ei) ei[(long)s * ldm + j] = e;
+      total += e;
+    }
+    double m = (e == e) ? e : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(&ei_max[s], (unsigned long long)__double_as_longlong(m));
+  }
+  if (ei_sum && j < M) ei_sum[j] += total;
+}
+
 // EI values leave the kernel as DOUBLE for both element types: in the deep-tail regime (late in a run max EI can be
 // 1e-50 and smaller) float32 storage flushes every candidate to zero and the argmax degenerates, while the reference
 // ranks those values in float64.
@@ -29,8 +66,13 @@ template <typename T>
 __global__ void __launch_bounds__(256) ei_sweep_kernel(int M, int S, int F, const T* __restrict__ mu,
                                                         const T* __restrict__ var, int ldm,
                                                         const T* __restrict__ best, const T* __restrict__ log_time,
-                                                        double* __restrict__ ei, double* __restrict__ ei_sum) {
+                                                        double* __restrict__ ei, double* __restrict__ ei_sum,
+                                                        unsigned long long* __restrict__ ei_max) {
   const int j = blockIdx.x * 256 + threadIdx.x;
+  if (ei_max) {            // per-sample maximum (bits of a non-negative double order like unsigned integers); small M only costs
+    ei_sweep_with_max<T>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ei_max, j);
+    return;
+  }
   if (j >= M) return;
   double total = 0.0;
   if (F == 1) {
@@ -83,7 +125,7 @@ __global__ void __launch_bounds__(256) ei_sweep_kernel(int M, int S, int F, cons
 
 template <typename T>
 int ei_sweep(int M, int S, int F, const T* mu, const T* var, int ldm, const T* best, const T* log_time, double* ei,
-             double* ei_sum, cudaStream_t st) {
+             double* ei_sum, unsigned long long* ei_max, cudaStream_t st) {
   if (M <= 0) return -1;
   if (S <= 0) return -2;
   if (F <= 0) return -3;
@@ -91,15 +133,33 @@ int ei_sweep(int M, int S, int F, const T* mu, const T* var, int ldm, const T* b
   if (!var) return -5;
   if (ldm < M) return -6;
   if (!best) return -7;
-  ei_sweep_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum);
+  if (ei_max) cudaMemsetAsync(ei_max, 0, sizeof(unsigned long long) * S, st);
+  ei_sweep_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(M, S, F, mu, var, ldm, best, log_time, ei, ei_sum, ei_max);
   count_launch();
   return check_launch("ei_sweep");
 }
 
 template int ei_sweep<float>(int, int, int, const float*, const float*, int, const float*, const float*, double*,
-                             double*, cudaStream_t);
+                             double*, unsigned long long*, cudaStream_t);
 template int ei_sweep<double>(int, int, int, const double*, const double*, int, const double*, const double*,
-                              double*, double*, cudaStream_t);
+                              double*, double*, unsigned long long*, cudaStream_t);
+
+// ei_sum[j] += sum_s ei[s][j]  (column sum of the per-sample EI matrix; fixed order -> deterministic)
+__global__ void __launch_bounds__(256) ei_colsum_kernel(int M, int S, const double* __restrict__ ei, int ldm,
+                                                         double* __restrict__ ei_sum) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= M) return;
+  double t = 0.0;
+  for (int s = 0; s < S; ++s) t += ei[(long)s * ldm + j];
+  ei_sum[j] += t;
+}
+int ei_colsum(int M, int S, const double* ei, int ldm, double* ei_sum, cudaStream_t st) {
+  if (M <= 0 || S <= 0) return -1;
+  if (!ei || !ei_sum || ldm < M) return -3;
+  ei_colsum_kernel<<<(M + 255) / 256, 256, 0, st>>>(M, S, ei, ldm, ei_sum);
+  count_launch();
+  return check_launch("ei_colsum");
+}
 
 // ------------------------------------------------------------------------------------------- top-k
 constexpr int kSlice = 4096;   // candidates per stage-1 block

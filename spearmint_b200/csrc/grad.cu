@@ -137,4 +137,76 @@ template int ei_grad_terms<float>(int, int, int, int, int, int, int, const float
 template int ei_grad_terms<double>(int, int, int, int, int, int, int, const double*, const double*, const double*,
                                    const double*, const double*, const double*, double*, cudaStream_t);
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// ML-II (GP.optimize_hypers, GP:181-292): the traces of grad_nlogprob (GP:238-264) for one setting of the hyper-parameters.
+// With  J = alpha alpha' - K^-1  (GP:246, "jacobian"), alpha = K^-1 (y - mean):
+//     out[0]     = sum_ij J_ij (corr_ij + 1e-6 delta_ij)                    -> grad[0] = 0.5 * out[0] * amp2      (GP:251)
+//     out[1]     = sum_i  J_ii                                              -> grad[1] = 0.5 * out[1] * noise     (GP:254)
+//     out[2 + d] = sum_ij J_ji gcorr_ij^d X[i][d]                           -> grad[2 + d] = -amp2 * out[2 + d]   (GP:258-259)
+// where gcorr_ij^d = dk/dr2(r2_ij) * (2 / ls_d) (X[i][d] - X[j][d]) / ls_d is the reference's grad_<kernel>(ls, comp)[i][j][d]
+// (GP:56-85, 102-132); the reference's exp(ls_d) factors cancel.  That last expression is what the reference hands to
+// L-BFGS-B as the length-scale gradient -- it is not the derivative of the likelihood, and it is reproduced as is.
+// The N x N x D gradient tensor of the reference is never materialised.  One thread per (i, j) pair, dimensions in chunks
+// of 8 accumulators, warp + atomic reduction (double atomics: the result is summed in a run-dependent order, ~1e-15).
+constexpr int kMllDC = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256) mll_grad_terms_kernel(int kind, int N, int D, const T* __restrict__ X,
+                                                              const T* __restrict__ inv_ls, const T* __restrict__ alpha,
+                                                              int lda, const T* __restrict__ Kinv, int ldk,
+                                                              double* __restrict__ out) {
+  const int s = blockIdx.z;
+  const int i = blockIdx.y * 16 + (threadIdx.x >> 4), j = blockIdx.x * 16 + (threadIdx.x & 15);
+  const bool act = i < N && j < N;
+  const T* il = inv_ls + (long)s * D;
+  const T* xi = X + (long)(act ? i : 0) * D;
+  const T* xj = X + (long)(act ? j : 0) * D;
+  double* o = out + (long)s * (D + 2);
+  T r2 = T(0);
+  for (int d = 0; d < D; ++d) { const T df = (xi[d] - xj[d]) * il[d]; r2 = fma(df, df, r2); }
+  // J_ji: row j of K^-1 (chol_solve column layout [f][n]) -- symmetric up to rounding
+  const T Jv = act ? alpha[(long)s * lda + i] * alpha[(long)s * lda + j] - Kinv[((long)s * N + j) * ldk + i] : T(0);
+  const T w = act ? Jv * dk_dr2<T>(kind, r2) * T(2) : T(0);
+  double t0 = act ? (double)(Jv * (kernel_of_r2<T>(kind, r2) + ((i == j) ? T(1e-6) : T(0)))) : 0.0;
+  double t1 = (act && i == j) ? (double)Jv : 0.0;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o2); t1 += __shfl_xor_sync(0xffffffffu, t1, o2); }
+  if (lane == 0) { atomicAdd(&o[0], t0); atomicAdd(&o[1], t1); }
+  for (int d0 = 0; d0 < D; d0 += kMllDC) {
+    double acc[kMllDC];
+#pragma unroll
+    for (int q = 0; q < kMllDC; ++q) {
+      const int d = d0 + q;
+      acc[q] = (d < D) ? (double)(w * (xi[d] - xj[d]) * il[d] * il[d] * xi[d]) : 0.0;
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o2);
+    }
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < kMllDC; ++q)
+        if (d0 + q < D) atomicAdd(&o[2 + d0 + q], acc[q]);
+  }
+}
+
+template <typename T>
+int mll_grad_terms(int kind, int N, int D, int S, const T* X, const T* inv_ls, const T* alpha, int lda, const T* Kinv,
+                   int ldk, double* out, cudaStream_t st) {
+  if (kind < 0 || kind > 3) return -1;
+  if (N <= 0) return -2;
+  if (D <= 0) return -3;
+  if (S <= 0) return -4;
+  if (!X || !inv_ls || !alpha || !Kinv || !out) return -5;
+  if (lda < N || ldk < N) return -8;
+  cudaMemsetAsync(out, 0, sizeof(double) * S * (D + 2), st);
+  mll_grad_terms_kernel<T><<<dim3((N + 15) / 16, (N + 15) / 16, S), 256, 0, st>>>(kind, N, D, X, inv_ls, alpha, lda, Kinv, ldk, out);
+  count_launch();
+  return check_launch("mll_grad_terms");
+}
+template int mll_grad_terms<float>(int, int, int, int, const float*, const float*, const float*, int, const float*, int,
+                                   double*, cudaStream_t);
+template int mll_grad_terms<double>(int, int, int, int, const double*, const double*, const double*, int, const double*, int,
+                                    double*, cudaStream_t);
+
 }  // namespace smk

@@ -13,8 +13,10 @@
 namespace smk {
 
 // ------------------------------------------------------------------------------------------ diag
-// Factor one NB x NB diagonal block and invert its factor, entirely on one SM (diag.cuh).  This kernel is the serial
-// spine of the factorisation: nblk launches per matrix, so its latency -- not its flops -- is what matters.
+// Factor one NB x NB diagonal block on one SM (diag.cuh).  This kernel is the serial spine of the factorisation: nblk
+// launches per matrix, so its latency -- not its flops -- is what matters.  It leaves the inverses of the four (two)
+// 32 x 32 diagonal pieces in the first NB x 32 elements of the block's winv slot; potrf_winv_kernel expands them to the
+// full W_jj = L_jj^-1 after the factorisation, off the spine.
 template <typename T>
 __global__ void __launch_bounds__(256) potrf_diag_kernel(int Npad, int jb, T* __restrict__ A,
                                                           T* __restrict__ winv, int* __restrict__ info) {
@@ -27,47 +29,44 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(int Npad, int jb, T* __
 }
 
 // ------------------------------------------------------------------------------------------ panel
-// L_Ij = A_Ij * W_jj^T  (one block per row tile I > jb)
+// L_Ij = A_Ij L_jj^-T by block substitution, 32 rows per CTA (diag.cuh: panel_sub_block); optional tf32 (hi, lo) copies
+// of the finished panel for the tcgen05 update.  grid = (rows below / 32, 1, S).
 template <typename T>
 __global__ void __launch_bounds__(256) potrf_panel_kernel(int Npad, int jb, T* __restrict__ A,
                                                            const T* __restrict__ winv, T* __restrict__ hi = nullptr,
                                                            T* __restrict__ lo = nullptr) {
-  using C = Cfg<T>;
-  constexpr int NB = C::NB;
-  __shared__ TileSmem<T> sm;
-  const int s = blockIdx.z, I = jb + 1 + blockIdx.x;
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  T* Aij = A + (long)s * Npad * Npad + (long)I * NB * Npad + (long)jb * NB;
-  const T* W = winv + ((long)s * (Npad / NB) + jb) * NB * NB;
-  T acc[C::TM][C::TN];
-#pragma unroll
-  for (int r = 0; r < C::TM; ++r)
-#pragma unroll
-    for (int c = 0; c < C::TN; ++c) acc[r][c] = T(0);
-  TileGemm<T, Lay::KContig, Lay::KContig, false>::run(acc, Aij, Npad, W, NB, NB, sm);
-  const long off = (long)s * Npad * Npad + (long)I * NB * Npad + (long)jb * NB;
-#pragma unroll
-  for (int r = 0; r < C::TM; ++r)
-#pragma unroll
-    for (int g = 0; g < C::TN / 4; ++g) {
-      V4<T> v;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v.v[e] = acc[r][g * 4 + e];
-      const long o = (long)tile_row(ty, r) * Npad + tile_col(tx, g * 4);
-      st4(Aij + o, v);
-      if (sizeof(T) == 4 && hi != nullptr) {     // tf32 hi/lo copies of the finished panel (operands of the tcgen05 update)
-        V4<T> h, l;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x = (float)v.v[e];
-          float xh = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-          h.v[e] = (T)xh;
-          l.v[e] = (T)(x - xh);
-        }
-        st4(hi + off + o, h);
-        st4(lo + off + o, l);
-      }
-    }
+  constexpr int NB = Cfg<T>::NB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int s = blockIdx.z;
+  const long base = (long)s * Npad * Npad;
+  const long off = base + ((long)(jb + 1) * NB + (long)blockIdx.x * 32) * Npad + (long)jb * NB;
+  const T* Ljj = A + base + (long)jb * NB * Npad + (long)jb * NB;
+  const T* wd = winv + ((long)s * (Npad / NB) + jb) * NB * NB;
+  panel_sub_block<T, NB>(A + off, Npad, Ljj, wd, hi ? hi + off : nullptr, lo ? lo + off : nullptr,
+                         reinterpret_cast<T*>(smem_raw));
+}
+
+// ------------------------------------------------------------------------------------------ full inverse blocks
+// W_jj = L_jj^-1 for every diagonal block of every sample at once (grid = (nblk, S)), after the factorisation.
+template <typename T>
+__global__ void __launch_bounds__(256) potrf_winv_kernel(int Npad, const T* __restrict__ A, T* __restrict__ winv) {
+  constexpr int NB = Cfg<T>::NB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int jb = blockIdx.x, s = blockIdx.y;
+  const T* Ljj = A + (long)s * Npad * Npad + (long)jb * NB * Npad + (long)jb * NB;
+  T* Wb = winv + ((long)s * (Npad / NB) + jb) * NB * NB;
+  winv_assemble_block<T, NB>(Ljj, Npad, Wb, Wb, reinterpret_cast<T*>(smem_raw));
+}
+
+template <typename T>
+static void potrf_set_attrs() {
+  constexpr int NB = Cfg<T>::NB;
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DiagSmem<T, NB>::bytes);
+  cudaFuncSetAttribute(potrf_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PanelSmem<T, NB>::bytes);
+  cudaFuncSetAttribute(potrf_winv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WinvSmem<T, NB>::bytes);
+  done = true;
 }
 
 // --------------------------------------------------------------------------------------- trailing
@@ -115,12 +114,8 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
   if (!winv) return -4;
   if (!info) return -5;
   const int nblk = Npad / NB;
-  const size_t dsm = DiagSmem<T, NB>::bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    attr_done = true;
-  }
+  const size_t dsm = DiagSmem<T, NB>::bytes, psm = PanelSmem<T, NB>::bytes, wsm = WinvSmem<T, NB>::bytes;
+  potrf_set_attrs<T>();
   cudaMemsetAsync(info, 0, sizeof(int) * S, st);
   // Block columns in pairs (jb, jb+1): factor jb, bring only column jb+1 up to date (rank NB), factor jb+1, then ONE
   // rank-2*NB update of everything to the right.
@@ -129,16 +124,18 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
     count_launch();
     int rem = nblk - jb - 1;
     if (rem <= 0) break;
-    potrf_panel_kernel<T><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, A, winv);
+    potrf_panel_kernel<T><<<dim3(rem * (NB / 32), 1, S), 256, psm, st>>>(Npad, jb, A, winv);
     potrf_trailing_kernel<T><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, 1, jb + 1, A);      // column jb+1 only
     potrf_diag_kernel<T><<<S, 256, dsm, st>>>(Npad, jb + 1, A, winv, info);
     count_launch(3);
     rem = nblk - jb - 2;
     if (rem <= 0) break;
-    potrf_panel_kernel<T><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb + 1, A, winv);
+    potrf_panel_kernel<T><<<dim3(rem * (NB / 32), 1, S), 256, psm, st>>>(Npad, jb + 1, A, winv);
     potrf_trailing_kernel<T><<<dim3(rem, rem, S), 256, 0, st>>>(Npad, jb, 2, jb + 2, A);   // rank 2*NB, columns >= jb+2
     count_launch(2);
   }
+  potrf_winv_kernel<T><<<dim3(nblk, S), 256, wsm, st>>>(Npad, A, winv);
+  count_launch();
   return check_launch("potrf_lower_batched");
 }
 
@@ -154,12 +151,8 @@ int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, fl
   if (S <= 0) return -2;
   if (!A || !winv || !info || !lhi || !llo) return -3;
   const int nblk = Npad / NB;
-  const size_t dsm = DiagSmem<float, NB>::bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(potrf_diag_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
-    attr_done = true;
-  }
+  const size_t dsm = DiagSmem<float, NB>::bytes, psm = PanelSmem<float, NB>::bytes, wsm = WinvSmem<float, NB>::bytes;
+  potrf_set_attrs<float>();
   cudaMemsetAsync(info, 0, sizeof(int) * S, st);
   for (int jb = 0; jb < nblk; jb += 2) {
     if (jb > 0) {
@@ -170,15 +163,17 @@ int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, fl
     count_launch();
     int rem = nblk - jb - 1;
     if (rem <= 0) break;
-    potrf_panel_kernel<float><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, A, winv, lhi, llo);
+    potrf_panel_kernel<float><<<dim3(rem * (NB / 32), 1, S), 256, psm, st>>>(Npad, jb, A, winv, lhi, llo);
     potrf_trailing_kernel<float><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, 1, jb + 1, A);
     potrf_diag_kernel<float><<<S, 256, dsm, st>>>(Npad, jb + 1, A, winv, info);
     count_launch(3);
     rem = nblk - jb - 2;
     if (rem <= 0) break;
-    potrf_panel_kernel<float><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb + 1, A, winv, lhi, llo);
+    potrf_panel_kernel<float><<<dim3(rem * (NB / 32), 1, S), 256, psm, st>>>(Npad, jb + 1, A, winv, lhi, llo);
     count_launch();
   }
+  potrf_winv_kernel<float><<<dim3(nblk, S), 256, wsm, st>>>(Npad, A, winv);
+  count_launch();
   return check_launch("potrf_lower_batched_tc");
 }
 

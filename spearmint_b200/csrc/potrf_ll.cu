@@ -3,11 +3,11 @@
 //
 // Round 1 ran this on the generic SIMT factorisation (NB = 64, 4 x 4 register tiles): 8.3 ms per N = 4096 matrix,
 // 2.8 TFLOP/s.  This file is the dedicated path:
-//   * NB = 128 block columns, right-looking, ONE step of look-ahead on two streams: while the rank-128 update of the
-//     trailing matrix (step j) runs, the next diagonal block and panel (step j + 1) are already being factored, so the
+//   * NB = 128 block columns in pairs, right-looking, look-ahead on two streams: while the rank-256 update of the
+//     trailing matrix (pair j) runs, the next pair's diagonal blocks and panels are already being factored, so the
 //     serial spine  diag -> panel -> column update  hides behind the N^3/3 flops;
-//   * diagonal blocks by the warp-synchronous single-SM kernel of diag.cuh;
-//   * panel (L_Ij = A_Ij W_jj^T) and trailing update (A_IK -= L_Ij L_Kj^T) as one tiled GEMM kernel on the fp64 tensor
+//   * diagonal blocks by the warp-synchronous single-SM kernel of diag.cuh, panels by its block substitution;
+//   * the trailing updates (A_IK -= L_Ij L_Kj^T) as one tiled GEMM kernel on the fp64 tensor
 //     path: mma.sync.m8n8k4.f64 (DMMA), operands staged by cp.async through a 3-stage shared-memory ring
 //     (row stride 20 doubles: conflict-free 8-byte fragment loads), 128 x 128 output tiles (32 x 64 per warp) for the
 //     update and 32-row tiles for the thin panel / look-ahead column so that even one matrix spreads over the SMs;
@@ -29,13 +29,26 @@ constexpr int KC = 16;         // k per stage
 constexpr int LDS = 20;        // shared row stride in doubles (16 + 4): fragment loads hit 16 distinct 8-byte banks
 constexpr int STAGES = 3;
 
+constexpr int WD = NB * 32;     // compact diagonal inverses of one block: [4][32][32]
+
 __global__ void __launch_bounds__(256) diag_kernel(int ld, int jb, double* __restrict__ A, long a_stride,
                                                     double* __restrict__ W, long w_stride, int* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
   double* Ab = A + (long)s * a_stride + (long)jb * NB * ld + (long)jb * NB;
-  diag_factor_block<double, NB>(Ab, ld, W + (long)s * w_stride + (long)jb * NB * NB, info ? info + s : nullptr, jb * NB,
+  diag_factor_block<double, NB>(Ab, ld, W + (long)s * w_stride + (long)jb * WD, info ? info + s : nullptr, jb * NB,
                                 reinterpret_cast<double*>(smem_raw));
+}
+
+// L_Ij = A_Ij L_jj^-T by block substitution, 32 rows per CTA; grid = (rows below / 32, 1, S)
+__global__ void __launch_bounds__(256) panel_kernel(int ld, int jb, double* __restrict__ A, long a_stride,
+                                                     const double* __restrict__ W, long w_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int s = blockIdx.z;
+  double* As = A + (long)s * a_stride;
+  panel_sub_block<double, NB>(As + ((long)(jb + 1) * NB + (long)blockIdx.x * 32) * ld + (long)jb * NB, ld,
+                              As + (long)jb * NB * ld + (long)jb * NB, W + (long)s * w_stride + (long)jb * WD, nullptr,
+                              nullptr, reinterpret_cast<double*>(smem_raw));
 }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -44,10 +57,7 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) { dmma_884(c, a, b); }
 
 // C[r0 + 0..BM)[c0 + 0..128) (op)= A[r0 + ..][0..K) * B[c0 + ..][0..K)^T, all row-major (k contiguous).
 //   sub = 1 : C -= A B^T (trailing / column update);  sub = 0 : C = A B^T (panel; C may alias A: each CTA reads its
@@ -69,10 +79,11 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(GemmArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* As = reinterpret_cast<double*>(smem_raw);           // [STAGES][BM][LDS]
   double* Bs = As + STAGES * BM * LDS;                         // [STAGES][128][LDS]
-  if (g.tri && blockIdx.y > blockIdx.x) return;
+
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp / WN, wn = warp % WN, gq = lane >> 2, t4 = lane & 3;
   const int r0 = g.row0 + blockIdx.x * BM, c0 = g.col0 + blockIdx.y * 128;
+  if (g.tri && c0 > r0 + BM - 1) return;            // the whole tile lies above the diagonal
   const double* A = g.A + (long)blockIdx.z * g.a_stride + (long)r0 * g.lda;
   const double* B = g.B + (long)blockIdx.z * g.b_stride + (long)(g.brow0 + blockIdx.y * 128) * g.ldb;
   double* C = g.C + (long)blockIdx.z * g.c_stride + (long)r0 * g.ldc + c0;
@@ -170,49 +181,50 @@ static Streams& streams() {
 // The launch sequence on (main, side); called directly or under stream capture.
 static int enqueue(int Npad, int S, double* A, double* W, int* info, Streams& ss) {
   const int nblk = Npad / NB;
-  const long as = (long)Npad * Npad, ws = (long)nblk * NB * NB;
-  const size_t dsm = DiagSmem<double, NB>::bytes;
+  const long as = (long)Npad * Npad, ws = (long)nblk * WD;
+  const size_t dsm = DiagSmem<double, NB>::bytes, psm = PanelSmem<double, NB>::bytes;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
     attr = true;
   }
   cudaStream_t m = ss.main, sd = ss.side;
   bool side_used = false;
-  for (int j = 0; j < nblk; ++j) {
-    // column j is complete: by the look-ahead column update of step j-1 (main) and the updates of steps <= j-2 (side,
-    // waited for before that column update was issued)
+  // Block columns in PAIRS (j, j+1).  Main stream (the spine): diag j, panel j, rank-128 update of column j+1, diag j+1,
+  // panel j+1, then the look-ahead: the rank-256 update of the NEXT pair's two columns.  Side stream: the rank-256 update
+  // of everything to the right of the next pair, overlapped with the next pair's spine.  Rank 256 halves the read-modify-
+  // write traffic of the trailing matrix per flop.
+  auto gemm_args = [&](int jcol, int K, int row_blk, int col_blk, int tri) {
+    GemmArgs g{};
+    g.A = A + (long)jcol * NB; g.lda = Npad; g.a_stride = as;
+    g.B = A + (long)jcol * NB; g.ldb = Npad; g.b_stride = as; g.brow0 = col_blk * NB;
+    g.C = A; g.ldc = Npad; g.c_stride = as;
+    g.K = K; g.row0 = row_blk * NB; g.col0 = col_blk * NB; g.sub = 1; g.tri = tri;
+    return g;
+  };
+  for (int j = 0, pair = 0; j < nblk; j += 2, ++pair) {
     diag_kernel<<<S, 256, dsm, m>>>(Npad, j, A, as, W, ws, info);
     count_launch();
-    const int rem = nblk - j - 1;                // block rows below
+    const int rem = nblk - j - 1;                // block rows below column j
     if (rem <= 0) break;
-    GemmArgs p{};
-    p.A = A + (long)j * NB; p.lda = Npad; p.a_stride = as;
-    p.B = W + (long)j * NB * NB; p.ldb = NB; p.b_stride = ws; p.brow0 = 0;
-    p.C = A + (long)j * NB; p.ldc = Npad; p.c_stride = as;
-    p.K = NB; p.row0 = (j + 1) * NB; p.col0 = 0; p.sub = 0; p.tri = 0;
-    launch_gemm<32>(p, rem * 4, 1, S, m);       // panel: L_Ij = A_Ij W_jj^T, 32-row tiles
-    cudaEventRecord(ss.panel[j & 1], m);
-    // look-ahead: bring block column j+1 up to date with respect to panel j on the main stream; the side stream's
-    // update of step j-1 also touches that column, so wait for it first
-    if (side_used) cudaStreamWaitEvent(m, ss.rest[(j - 1) & 1], 0);
-    GemmArgs c{};
-    c.A = A + (long)j * NB; c.lda = Npad; c.a_stride = as;
-    c.B = A + (long)j * NB; c.ldb = Npad; c.b_stride = as; c.brow0 = (j + 1) * NB;
-    c.C = A; c.ldc = Npad; c.c_stride = as;
-    c.K = NB; c.row0 = (j + 1) * NB; c.col0 = (j + 1) * NB; c.sub = 1; c.tri = 0;
-    launch_gemm<32>(c, rem * 4, 1, S, m);
+    panel_kernel<<<dim3(rem * 4, 1, S), 256, psm, m>>>(Npad, j, A, as, W, ws);           // L_Ij = A_Ij L_jj^-T
+    launch_gemm<32>(gemm_args(j, NB, j + 1, j + 1, 0), rem * 4, 1, S, m);                 // column j+1 -= L_Ij L_(j+1)j^T
+    diag_kernel<<<S, 256, dsm, m>>>(Npad, j + 1, A, as, W, ws, info);
+    count_launch(3);
+    const int rem2 = nblk - j - 2;               // block rows below column j+1
+    if (rem2 <= 0) break;
+    panel_kernel<<<dim3(rem2 * 4, 1, S), 256, psm, m>>>(Npad, j + 1, A, as, W, ws);
+    cudaEventRecord(ss.panel[pair & 1], m);
+    // look-ahead: the next pair's columns (j+2, j+3) with respect to panels j and j+1; the side stream's update of the
+    // previous pair also wrote those columns, so wait for it first
+    if (side_used) cudaStreamWaitEvent(m, ss.rest[(pair - 1) & 1], 0);
+    launch_gemm<32>(gemm_args(j, 2 * NB, j + 2, j + 2, 1), rem2 * 4, rem2 >= 2 ? 2 : 1, S, m);
     count_launch(2);
-    if (rem >= 2) {
-      // the rest of the trailing matrix (block columns >= j+2) on the side stream
-      cudaStreamWaitEvent(sd, ss.panel[j & 1], 0);
-      GemmArgs r{};
-      r.A = A + (long)j * NB; r.lda = Npad; r.a_stride = as;
-      r.B = A + (long)j * NB; r.ldb = Npad; r.b_stride = as; r.brow0 = (j + 2) * NB;
-      r.C = A; r.ldc = Npad; r.c_stride = as;
-      r.K = NB; r.row0 = (j + 2) * NB; r.col0 = (j + 2) * NB; r.sub = 1; r.tri = 1;
-      launch_gemm<128>(r, rem - 1, rem - 1, S, sd);
-      cudaEventRecord(ss.rest[j & 1], sd);
+    if (rem2 > 2) {                              // everything to the right of the next pair, on the side stream
+      cudaStreamWaitEvent(sd, ss.panel[pair & 1], 0);
+      launch_gemm<128>(gemm_args(j, 2 * NB, j + 4, j + 4, 1), rem2 - 2, rem2 - 2, S, sd);
+      cudaEventRecord(ss.rest[pair & 1], sd);
       count_launch();
       side_used = true;
     }
@@ -231,7 +243,7 @@ static std::map<cudaGraphExec_t, int>& launches_per_graph() {
   return m;
 }
 
-size_t potrf_ll_workspace_bytes(int Npad, int S) { return (size_t)S * (Npad / ll::NB) * ll::NB * ll::NB * sizeof(double); }
+size_t potrf_ll_workspace_bytes(int Npad, int S) { return (size_t)S * (Npad / ll::NB) * ll::WD * sizeof(double); }
 
 // A: [S][Npad][Npad] (lower triangle in/out), W: workspace, info[S].  Npad % 128 == 0.
 // use_graph: capture the sequence once per (A, W, info, Npad, S) on internal streams and replay it behind `st`.

@@ -4,7 +4,7 @@
 // Same contract as predict.cu (reference spans OPT:536, 544, 547-548), different dataflow:
 //   1. trtri   : Linv = L^-1 explicitly (row-block recurrence on tcgen05, mode 3; SIMT version for small N) -- removes the
 //                row-block dependency chain of the triangular solve: beta = Linv * Kx is one dense (lower-trapezoidal)
-//                contraction.  Kept as a tf32 (hi, lo) pair of float arrays (hi = x & 0xffffe000, lo = x - hi).
+//                contraction.  Kept as a tf32 (hi, lo) pair of float arrays (hi = tf32 round-to-nearest of x, lo = x - hi, exact).
 //   2. pack    : GEMM-operand copy of Linv: per-sample power-of-two scale 2^eb (largest |entry| -> [2^14, 2^15)) and the
 //                round-to-nearest fp16 (hi, lo) pair (linv_pack_f16).
 //   3. kxt     : Kxt[s][c][n] = amp2 k(X_n, C_c) * 2^ea for a chunk of candidates, candidate-major (n contiguous, i.e.
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, 2) trtri_update_kernel(int Npad, int ldx,
     }
 }
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }   // round-to-nearest split (common.cuh)
 
 // hi/lo split of the lower triangle (upper triangle and padding are written as zeros)
 __global__ void split_lower_kernel(int Npad, int ld, long total, const float* __restrict__ X, float* __restrict__ hi,
@@ -643,7 +643,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   v[e] = -__uint_as_float(r[j + e]);
-                  hh[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                  hh[e] = tf32_rn(v[e]);
                   ll[e] = v[e] - hh[e];
                 }
                 *reinterpret_cast<float4*>(p.xhi + xr + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);

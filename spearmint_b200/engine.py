@@ -142,6 +142,20 @@ class Factor(object):
                                    ptr(tmp), eng.stream()), "linv_alpha")
         return alpha
 
+    def guard(self):
+        """[S] float32 on the device: estimated relative error of the predictive variance at a candidate sitting on an
+        observed point if the explicit inverse is used (csrc/guard.cu)."""
+        eng, L = self.eng, _lib.lib()
+        hi, lo, Np = self.linv()
+        S = self.hb.S
+        g = torch.empty((S,), dtype=torch.float32, device=eng.device)
+        nb = L.smk_tc_guard_workspace_bytes(Np, S)
+        ws = eng.take((nb,), torch.uint8)
+        eng.give(ws)
+        check(L.smk_tc_guard_f32(self.N, self.Npad, Np, S, ptr(self.L), ptr(hi), ptr(lo), ptr(self.hb.amp2),
+                                 ptr(self.hb.noise), ptr(g), ptr(ws), nb, eng.stream()), "tc_guard")
+        return g
+
     def check_pd(self):
         """The reference lets spla.cholesky raise LinAlgError (SURVEY 8b 'Errors'); so do we."""
         info = self.info.cpu().numpy()
@@ -158,6 +172,10 @@ class Factor(object):
         eng, hb = self.eng, self.hb
         S, dt, dev = hb.S, eng.dtype, eng.device
         n = self.N if n_lead is None else n_lead
+        rb, nb_ = (4, 128) if dt == torch.float32 else (2, 64)
+        if eng.esize * (rb * self.Npad + rb * nb_ + (256 // nb_) * rb * nb_) > 227 * 1024:
+            raise _lib.SmkError("chol_solve keeps its right-hand sides in shared memory: N = %d exceeds its limit (about "
+                                "%d for this element type); use the explicit-inverse path" % (self.N, 227 * 1024 // (eng.esize * rb)))
         alpha = torch.empty((S, F, self.Npad), dtype=dt, device=dev) if want_alpha else None
         sld = torch.empty((S,), dtype=dt, device=dev) if want_logdet else None
         quad = torch.empty((S, F), dtype=dt, device=dev) if want_quad else None
@@ -201,7 +219,11 @@ class GPEIEngine(object):
             self.predict_impl = "simt"
         # N^3 steps (Cholesky trailing update, triangular inverse): "tc" = tcgen05 3xTF32 left-looking variants
         self.factor_impl = os.environ.get("SMK_FACTOR_IMPL", "tc" if self.predict_impl == "tc" else "simt")
+        # accuracy guard of the explicit-inverse (tensor-core) predict (csrc/guard.cu, _guarded_impl): a hyper-sample whose
+        # estimated EI error exceeds this fraction of its largest EI is re-evaluated in float64 (0 disables the guard)
+        self.guard_threshold = float(os.environ.get("SMK_TC_GUARD", "1.5e-3"))
         self.last = {}
+        self.last_guard = None
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
         self._pool = {}      # (shape, dtype) -> free tensors: the big per-call buffers are recycled, never re-allocated
         self._helper64 = None
@@ -357,18 +379,40 @@ class GPEIEngine(object):
                                        self.stream()), "cross_mean")
         return mu
 
-    def ei_sweep(self, M, S, F, mu, var, ldm, best, log_time=None, want_ei=True, ei_sum=None):
+    def ei_sweep(self, M, S, F, mu, var, ldm, best, log_time=None, want_ei=True, ei_sum=None, ei_max=None, accumulate=True):
         dt = self.dtype
         ei = torch.empty((S, ldm), dtype=torch.float64, device=self.device) if want_ei else None   # EI is always double
-        if ei_sum is None:
+        if ei_sum is None and accumulate:
             ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=self.device)
         check(fn("smk_ei_sweep", dt)(M, S, F, ptr(mu), ptr(var), ldm, ptr(best), ptr(log_time), ptr(ei),
-                                     ptr(ei_sum), self.stream()), "ei_sweep")
+                                     ptr(ei_sum) if accumulate else None, ptr(ei_max), self.stream()), "ei_sweep")
         return ei, ei_sum
 
     def topk(self, score, M, k):
-        """Indices of the k largest scores, ascending (argsort(score)[-k:], OPT:270; [-1] is the argmax, OPT:294)."""
+        """Indices of the k largest scores, ascending (argsort(score)[-k:], OPT:270; [-1] is the argmax, OPT:294).
+        The device selection handles k <= 256 per call; larger k (the reference accepts any grid_subset) takes several
+        rounds, each masking what the previous ones took."""
         dt = score.dtype                      # EI scores are float64 (see ei_sweep)
+        K = 256
+        if k <= K:
+            idx, val = self._topk_once(score, M, k)
+        else:
+            work = score[:M].clone()
+            parts_i, parts_v = [], []
+            left = k
+            while left > 0:
+                kk = min(K, left)
+                i, v = self._topk_once(work, M, kk)           # ascending
+                parts_i.append(i)
+                parts_v.append(v)
+                work[i.long()] = float("-inf")
+                left -= kk
+            idx = torch.cat(parts_i[::-1])                   # later rounds hold smaller scores
+            val = torch.cat(parts_v[::-1])
+        return idx, val
+
+    def _topk_once(self, score, M, k):
+        dt = score.dtype
         nb = _lib.lib().smk_topk_workspace_bytes(M, k)
         ws = torch.empty((nb,), dtype=torch.uint8, device=self.device)
         idx = torch.empty((k,), dtype=torch.int32, device=self.device)
@@ -383,6 +427,9 @@ class GPEIEngine(object):
         hb) of tensors already in HBM (the bench's `value` leg)."""
         p = Prepared()
         p.kind = kind
+        p.host = dict(hyper_samples=hyper_samples, comp=comp, pend=pend, vals=vals, normals=normals,
+                      time_hyper_samples=time_hyper_samples, durs_log=durs_log)
+        p.gbound, p.flagged, p.prep64 = None, None, None
         P = 0 if pend is None else int(pend.shape[0])
         if resident is not None:
             Xo, yd, best_val = resident["X"], resident["y"], resident["best"]
@@ -402,11 +449,12 @@ class GPEIEngine(object):
             fac = self.factor(kind, Xo, hb)
             self._t1("cov_potrf", t)
             t = self._t0()
-            if self.predict_impl == "tc":
+            p.impl = self._guarded_impl(fac, p)
+            if p.impl == "tc":
                 alpha = fac.alpha_via_linv(yd)       # explicit inverse (trtri, once per factor batch) + two mat-vecs
             else:
                 alpha, _, _ = fac.solve(yd, F=1)
-            self._t1("linv_alpha" if self.predict_impl == "tc" else "chol_solve", t)
+            self._t1("linv_alpha" if p.impl == "tc" else "chol_solve", t)
             p.fac, p.alpha, p.F = fac, alpha, 1
             p.bests = torch.full((hb.S, 1), best_val, dtype=self.dtype, device=self.device)
             p.bests_host = np.full((hb.S, 1), best_val)
@@ -417,6 +465,25 @@ class GPEIEngine(object):
             self._prepare_pending(p, kind, hb, hyper_samples, Xo, self.to_dev(pend), yd, np.asarray(comp, float),
                                   np.asarray(pend, float), np.asarray(vals, float), np.asarray(normals, float))
         return p
+
+    def _guarded_impl(self, fac, p):
+        """Arms the accuracy guard of the explicit-inverse (tensor-core) predict for this factor batch.
+
+        csrc/guard.cu measures g_s = relative variance error the path makes for a candidate sitting on the data.  The EI
+        of such a candidate (s^2 ~ noise + jitter, u ~ 0) then moves by about  0.5 phi(0) g sqrt(noise + 1e-6 amp2), which
+        is kept per sample as the absolute bound p.gbound[s].  After every sweep the bound is compared with the largest EI
+        of the sample (ei_prepared): a sample whose bound exceeds guard_threshold * max EI is re-evaluated on the float64
+        engine.  Well-conditioned problems (the headline: bound / max EI ~ 6e-4) never trip it; smooth low-dimensional ones
+        (C2, C4: ~5e-3) do.  Measured against actual errors in profiles/r02_precision_guard.md."""
+        p.gbound, p.flagged, p.prep64 = None, None, None
+        if self.predict_impl != "tc" or self.dtype != torch.float32:
+            return self.predict_impl
+        if self.guard_threshold > 0:
+            g = fac.guard().double().cpu().numpy()                       # one small read per factor batch
+            hb = fac.hb
+            p.gbound = 0.2 * g * np.sqrt(hb.host_noise + JITTER * hb.host_amp2)
+            self.last_guard = dict(g_max=float(g.max()), bound_max=float(p.gbound.max()))
+        return "tc"
 
     def _prepare_pending(self, p, kind, hb, hyper_samples, Xo, Pd, yd, comp, pend, vals, normals):
         """Pending-fantasy prologue (OPT:558-603) for one chunk of hyper-samples.
@@ -461,11 +528,13 @@ class GPEIEngine(object):
         fant_d = self.to_dev(fant)                                                # [S][F][N+P]
         alpha_f, _, _ = fac.solve(fant_d, F=F, y_stride=F * (N + P), ldy=N + P)   # OPT:603
         p.fac, p.alpha, p.F = fac, alpha_f, F
+        p.impl = self._guarded_impl(fac, p)
         p.bests, p.bests_host = self.to_dev(bests), bests
         p.pred_alpha = torch.zeros((S, fac.Npad), dtype=self.dtype, device=self.device)
 
-    def ei_prepared(self, p, Cd, want_matrix=True, ei_sum=None):
-        """EI of every candidate in Cd for every sample of a Prepared chunk.  Returns (ei [S][ldm] | None, ei_sum)."""
+    def ei_prepared(self, p, Cd, want_matrix=True, ei_sum=None, cand_host=None):
+        """EI of every candidate in Cd for every sample of a Prepared chunk.  Returns (ei [S][ldm] | None, ei_sum).
+        ``cand_host``: the float64 candidates behind Cd (used only if the accuracy guard re-evaluates a sample)."""
         kind, fac, hb = p.kind, p.fac, p.hb
         M = Cd.shape[0]
         ldm = _ceil(M, 128)
@@ -474,19 +543,57 @@ class GPEIEngine(object):
             tfac, ta = p.time
             log_time = self.cross_mean(kind, tfac, Cd, ta, 1).view(tfac.hb.S, ldm)
         t = self._t0()
-        if p.P > 0 and self.predict_impl == "tc" and p.F > 1:
-            _, var, _, mu = self.predict(kind, fac, Cd, p.pred_alpha, alpha_f=p.alpha, F=p.F)   # OPT:605-610
+        impl = getattr(p, "impl", None) or self.predict_impl
+        if p.P > 0 and impl == "tc" and p.F > 1:
+            _, var, _, mu = self.predict(kind, fac, Cd, p.pred_alpha, impl=impl, alpha_f=p.alpha, F=p.F)   # OPT:605-610
         else:
-            mu, var, _ = self.predict(kind, fac, Cd, p.pred_alpha)                 # OPT:544-548 / 605-610
+            mu, var, _ = self.predict(kind, fac, Cd, p.pred_alpha, impl=impl)      # OPT:544-548 / 605-610
             if p.P > 0:
                 mu = self.cross_mean(kind, fac, Cd, p.alpha, p.F)                  # OPT:609
             else:
                 mu = mu.view(hb.S, 1, ldm)
         self._t1("predict", t)
         t = self._t0()
-        out = self.ei_sweep(M, hb.S, p.F, mu, var, ldm, p.bests, log_time, want_matrix, ei_sum)
+        guarded = p.gbound is not None and p.host.get("comp") is not None
+        if not guarded:
+            out = self.ei_sweep(M, hb.S, p.F, mu, var, ldm, p.bests, log_time, want_matrix, ei_sum)
+            self._t1("ei_sweep", t)
+            return out
+        # ---- guarded sweep: per-sample EI and its maximum first, the sum over samples after the check
+        if ei_sum is None:
+            ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=self.device)
+        ei_max = torch.empty((hb.S,), dtype=torch.int64, device=self.device)
+        ei, _ = self.ei_sweep(M, hb.S, p.F, mu, var, ldm, p.bests, log_time, True, None, ei_max=ei_max, accumulate=False)
         self._t1("ei_sweep", t)
-        return out
+        if p.flagged is None:                                             # decided on the first sweep of this factor batch
+            mx = ei_max.cpu().numpy().view(np.float64)
+            p.flagged = [int(s) for s in np.nonzero(p.gbound > self.guard_threshold * mx)[0]]
+            self.last_guard = dict(self.last_guard or {}, flagged=len(p.flagged), S=hb.S,
+                                   worst_ratio=float(np.max(p.gbound / np.maximum(mx, 1e-300))))
+        if p.flagged:
+            self._reevaluate_f64(p, Cd, cand_host, ei)
+        check(_lib.lib().smk_ei_colsum(M, hb.S, ptr(ei), ldm, ptr(ei_sum), self.stream()), "ei_colsum")
+        return (ei if want_matrix else None), ei_sum
+
+    def _reevaluate_f64(self, p, Cd, cand_host, ei):
+        """Rows p.flagged of ei (per-sample EI of this candidate set) recomputed by the float64 build of the same kernels
+        (blocked-substitution predict): what the tensor-core path cannot deliver for these samples, the reference's own
+        precision can.  The float64 factors are built once per Prepared and reused by later sweeps."""
+        h64 = self.helper64()
+        H = p.host
+        sel = p.flagged
+        if cand_host is None:
+            cand_host = Cd.double().cpu().numpy()
+        if p.prep64 is None:
+            hs = [H["hyper_samples"][s] for s in sel]
+            ths = None if H["time_hyper_samples"] is None else [H["time_hyper_samples"][s] for s in sel]
+            nrm = H["normals"]
+            if nrm is not None and np.ndim(nrm) == 3:
+                nrm = np.asarray(nrm)[sel]
+            p.prep64 = h64.prepare(p.kind, hs, H["comp"], H["pend"], H["vals"], nrm, ths, H["durs_log"])
+            p.prep64.fac.check_pd()
+        e64, _ = h64.ei_prepared(p.prep64, h64.to_dev(cand_host), True, None)
+        ei[torch.as_tensor(sel, device=self.device)] = e64
 
     # ------------------------------------------------------------------ whole path
     def ei_over_hypers_device(self, kind, hyper_samples, comp, pend, cand, vals, normals=None,
@@ -513,7 +620,7 @@ class GPEIEngine(object):
             prep = self.prepare(kind, hyper_samples[s0:s0 + chunk], comp, pend, vals, nrm,
                                 None if time_hyper_samples is None else time_hyper_samples[s0:s0 + chunk],
                                 durs_log, resident=r)
-            ei, _ = self.ei_prepared(prep, Cd, want_matrix, ei_sum)
+            ei, _ = self.ei_prepared(prep, Cd, want_matrix, ei_sum, cand_host=cand)
             prep.fac.check_pd()     # one host sync per chunk, after everything is queued
             if want_matrix:
                 ei_all[s0:s0 + prep.S] = ei

@@ -41,6 +41,9 @@ class OracleBackend(object):
                 return out
         return Batched()
 
+    def optimize_hypers(self, kind, comp, vals):
+        return O.gp_optimize_hypers(kind, comp, vals)
+
     def grid_state(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None, durs_log=None):
         st = _State()
         st.kind, st.hs, st.comp, st.pend, st.vals, st.normals = kind, list(hyper_samples), comp, pend, vals, normals

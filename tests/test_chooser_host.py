@@ -173,3 +173,17 @@ def test_speculative_batched_sampler_keeps_the_chain(name, tmp_path):
     assert u0 == u1
     assert (r0[0], tuple(r0[1])) == (r1[0], tuple(r1[1])) if isinstance(r0, tuple) else r0 == r1
     assert b1.batches < 0.5 * b0.loglik_calls          # sequential depth at least halved
+
+
+@pytest.mark.parametrize("name", ["mll_d3_m52", "mll_d5_ardse", "mll_d2_m32"])
+def test_gpei_ml2_branch_host_logic(name, tmp_path):
+    """GPEIChooserB200 with mcmc_iters=0 (GPEI:156-176, 348-361) on the oracle backend: same optimum, same proposal as the
+    reference's next()."""
+    from spearmint_b200.chooser import GPEIChooserB200 as mod
+    g = load(name)
+    ch = mod.init(str(tmp_path), "covar=%s,mcmc_iters=0" % str(g["kind"]))
+    ch._backend = OracleBackend()
+    np.random.seed(5)
+    ret = ch.next(g["grid"], g["values"], None, g["candidates"], np.array([], dtype=int), g["complete"])
+    assert ret == int(g["next_index"])
+    np.testing.assert_allclose(np.hstack([ch.mean, ch.noise, ch.amp2, ch.ls]), g["next_hypers"], rtol=1e-6)

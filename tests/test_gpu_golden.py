@@ -120,3 +120,38 @@ def test_ei_path_medium_n_vs_oracle(engines, D, N, M):
             assert np.abs(e - r).max() <= 5e-3 * r.max(), (s, np.abs(e - r).max(), r.max())
     # the proposal: argmax of the mean over samples (OPT:294) must be the reference's
     assert int(np.argmax(ei.mean(axis=1))) == int(np.argmax(ref.mean(axis=1)))
+
+
+def test_pending_point_next_to_an_observation(engines):
+    """a pending point 1e-3 away from an observed one (the jitter cloud next() itself proposes) with tiny
+    noise.  pend_K = Lpp Lpp' - noise I then cancels down to the 1e-6 amp2 jitter; a float32 joint factor cannot hold that,
+    the reference's float64 can -- so the conditional is formed in float64 (engine._prepare_pending) and must neither
+    raise LinAlgError nor leave the stated tolerance."""
+    from oracle import gp_oracle as O
+    rs = np.random.RandomState(42)
+    D, N, M, F = 3, 60, 300, 20
+    comp, cand = rs.rand(N, D), rs.rand(M, D)
+    y = np.sin(3 * comp).sum(1)
+    vals = (y - y.mean()) / y.std()
+    pend = np.vstack([comp[7] + 1e-3 * rs.randn(D), rs.rand(D)])
+    hs = [(0.0, 1e-6, 1.0, rs.uniform(0.5, 1.5, D)), (0.1, 1e-6, 0.8, rs.uniform(0.5, 1.5, D))]
+    normals = rs.randn(2, F)
+    ref = O.ei_over_hypers("Matern52", hs, comp, pend, cand, vals, normals)
+    ei = engines["f32"].ei_over_hypers("Matern52", hs, comp, pend, cand, vals, normals)
+    _check(ei, ref, "f32")
+    ei64 = engines["f64"].ei_over_hypers("Matern52", hs, comp, pend, cand, vals, normals)
+    _check(ei64, ref, "f64")
+
+
+def test_topk_beyond_256(engines):
+    """grid_subset > 256 (the reference accepts any value): several selection rounds, same answer as numpy."""
+    import torch
+    eng = engines["f32"]
+    rs = np.random.RandomState(3)
+    score = rs.rand(5000)
+    score[100] = score[200]                                     # a tie: the lower index ranks higher
+    d = torch.from_numpy(score).to(eng.device)
+    idx, val = eng.topk(d, 5000, 700)
+    ref = np.lexsort((-np.arange(5000), score))[-700:]
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    assert np.array_equal(val.cpu().numpy(), score[ref])

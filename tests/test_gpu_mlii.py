@@ -1,0 +1,62 @@
+"""-m gpu: ML-II hyper-parameters (row f3) -- spearmint_b200.gp.GP against values frozen from the reference's
+gp.GP.optimize_hypers (gp.py:181-292; tests/golden/make_golden_mll.py): objective and 'gradient' at fixed points (the
+GPU float64 likelihood + smk_mll_grad_terms), the optimum L-BFGS-B reaches, and GPEIChooser.next() with mcmc_iters=0."""
+import numpy as np
+import pytest
+
+from tests.helpers import load
+
+pytestmark = pytest.mark.gpu
+CASES = ["mll_d3_m52", "mll_d5_ardse", "mll_d2_m32"]
+
+
+@pytest.fixture(scope="module")
+def backend():
+    from spearmint_b200.backend import DeviceBackend
+    return DeviceBackend()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_value_and_gradient_terms(backend, name):
+    import torch
+    from spearmint_b200.gp import GP
+    g = load(name)
+    comp, vals, kind = g["grid"][g["complete"]], g["values"][g["complete"]], str(g["kind"])
+    gp = GP(kind, engine=backend.eng64)
+    gp.real_init(comp.shape[1], vals)
+    eng = backend.eng64
+    cd, yd = eng.to_dev(comp), eng.to_dev(vals)
+    eye = torch.eye(comp.shape[0], dtype=eng.dtype, device=eng.device)
+    for pt, f_ref, g_ref in zip(g["pts"], g["f"], g["g"]):
+        f, gr = gp.value_grad(pt, cd, yd, eye, np.mean(vals))
+        np.testing.assert_allclose(f, f_ref, rtol=1e-10, atol=1e-9)
+        np.testing.assert_allclose(gr, g_ref, rtol=1e-7, atol=1e-8 * max(1.0, np.abs(g_ref).max()))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_optimum_and_logprob(backend, name):
+    from oracle import gp_oracle as O
+    from spearmint_b200.gp import GP
+    g = load(name)
+    comp, vals, kind = g["grid"][g["complete"]], g["values"][g["complete"]], str(g["kind"])
+    gp = GP(kind, engine=backend.eng64)
+    gp.real_init(comp.shape[1], vals)
+    gp.optimize_hypers(comp, vals)
+    np.testing.assert_allclose([gp.mean, gp.noise, gp.amp2], [g["opt_mean"], g["opt_noise"], g["opt_amp2"]], rtol=1e-5)
+    np.testing.assert_allclose(gp.ls, g["opt_ls"], rtol=1e-5)
+    np.testing.assert_allclose(gp.logprob(comp, vals), O.gp_logprob(kind, gp.mean, gp.noise, gp.amp2, gp.ls, comp, vals),
+                               rtol=1e-10)
+    K = gp.cov(comp)
+    np.testing.assert_allclose(K, O.cov(kind, gp.amp2, gp.ls, comp), rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gpei_chooser_ml2_next(backend, name, tmp_path):
+    from spearmint_b200.chooser import GPEIChooserB200 as mod
+    g = load(name)
+    ch = mod.init(str(tmp_path), "covar=%s,mcmc_iters=0" % str(g["kind"]))
+    ch._backend = backend
+    np.random.seed(5)
+    ret = ch.next(g["grid"], g["values"], None, g["candidates"], np.array([], dtype=int), g["complete"])
+    assert ret == int(g["next_index"])
+    np.testing.assert_allclose(np.hstack([ch.mean, ch.noise, ch.amp2, ch.ls]), g["next_hypers"], rtol=1e-5)

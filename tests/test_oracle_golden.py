@@ -91,3 +91,31 @@ def test_ei_per_second_matches_reference(name):
         np.testing.assert_allclose(ov, g["overall_ei"], rtol=RTOL, atol=1e-14)
     assert np.all(g["overall_ei"][:, 1:] == 0.0)
     assert int(g["n_time_samples"]) > S  # stale burn-in time samples are never cleared (PSEC:199)
+
+
+def test_sobol_oracle_matches_reference_generator():
+    """Row f4: the numpy restatement of sobol_lib.i4_sobol_generate against golden points of the real generator."""
+    from oracle import sobol_oracle as SO
+    g = load("sobol")
+    for i in range(7):
+        m, n, skip = (int(x) for x in g["case%d_args" % i])
+        assert np.array_equal(SO.i4_sobol_generate(m, n, skip), g["case%d_pts" % i]), (m, n, skip)
+
+
+MLL_CASES = ["mll_d3_m52", "mll_d5_ardse", "mll_d2_m32"]
+
+
+@pytest.mark.parametrize("name", MLL_CASES)
+def test_mll_oracle_matches_reference_optimize_hypers(name):
+    """Row f3: GP.optimize_hypers' objective, its 'gradient' (incl. the reference's length-scale expression) and the
+    optimum, against values frozen from the real gp.py (tests/golden/make_golden_mll.py)."""
+    g = load(name)
+    comp, vals, kind = g["grid"][g["complete"]], g["values"][g["complete"]], str(g["kind"])
+    mean = np.mean(vals)
+    for pt, f_ref, g_ref in zip(g["pts"], g["f"], g["g"]):
+        f, gr = O.mll_value_grad(kind, pt, comp, vals, mean)
+        np.testing.assert_allclose(f, f_ref, rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(gr, g_ref, rtol=1e-8, atol=1e-9)
+    m, noise, amp2, ls = O.gp_optimize_hypers(kind, comp, vals)
+    np.testing.assert_allclose([m, noise, amp2], [g["opt_mean"], g["opt_noise"], g["opt_amp2"]], rtol=1e-6)
+    np.testing.assert_allclose(ls, g["opt_ls"], rtol=1e-6)

@@ -28,4 +28,7 @@ for prec in ("f32", "f64"):
     ei = eng.ei_over_hypers(bench.KIND, hs, comp, pend, cand, vals)
     out[prec] = [float(np.abs(ei[:, s] - ref[:, s]).max() / ref[:, s].max()) for s in range(len(hs))]
     out[prec + "_argmax_ok"] = bool(np.argmax(ei.mean(1)) == np.argmax(ref.mean(1)))
+    if prec == "f32":
+        out["guard"] = eng.last_guard
+        out["guard_threshold"] = eng.guard_threshold
 print(json.dumps(out))
