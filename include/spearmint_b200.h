@@ -147,12 +147,13 @@ int smk_trtri_split_tc_f32(int Npad, int Np, int S, const float* L, const float*
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream);
 /* Accuracy guard of the tensor-core path (csrc/guard.cu): g[s] = estimated RELATIVE error of the predictive variance of a
- * candidate sitting on an observed point, measured by pushing 4 columns of K = L L^T through the explicit inverse
+ * candidate sitting on an observed point, measured by pushing 4 columns of K = L L^T (rows[]: the caller's incumbents) through the explicit inverse
  * (float64 accumulation):  | |Linv (L v)|^2 - |v|^2 | / (noise + 1e-6 amp2),  v = a row of L.  The caller routes the
  * batch to smk_predict_f32 (blocked substitution) when it exceeds its threshold.                                   */
 size_t smk_tc_guard_workspace_bytes(int Np, int S);
 int smk_tc_guard_f32(int N, int Npad, int Np, int S, const float* L, const float* linv_hi, const float* linv_lo,
-                     const float* amp2, const float* noise, float* g, void* workspace, size_t workspace_bytes, void* stream);
+                     const float* amp2, const float* noise, const int* rows /* [4] probe rows (device) */, float* g,
+                     void* workspace, size_t workspace_bytes, void* stream);
 size_t smk_predict_tc_workspace_bytes(int Np, int M, int S, int F);
 /* F > 1 with alpha_f [S][F][Npad_alpha] and mu_f [S][F][ldm] non-NULL: additionally the fantasy means
  * mu_f[s][f][j] = cov(X, C_j)' alpha_f[s][f] + mean[s]  (OPT:609) as a second tcgen05 GEMM on the same Kxt chunk. */

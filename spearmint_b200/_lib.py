@@ -54,7 +54,7 @@ SIGNATURES = {
     "smk_potrf_loglik_workspace_bytes": ([_i, _i], _sz),
     "smk_potrf_loglik_f64": ([_i, _i, _p, _p, _sz, _p, _i, _p], _i),
     "smk_tc_guard_workspace_bytes": ([_i, _i], _sz),
-    "smk_tc_guard_f32": ([_i] * 4 + [_p] * 7 + [_sz, _p], _i),
+    "smk_tc_guard_f32": ([_i] * 4 + [_p] * 8 + [_sz, _p], _i),
     "smk_ei_colsum": ([_i, _i, _p, _i, _p, _p], _i),
     "smk_tc_np": ([_i], _i),
     "smk_trtri_workspace_bytes": ([_i, _i], _sz),

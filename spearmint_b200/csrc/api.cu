@@ -1,6 +1,7 @@
 // api.cu -- extern "C" surface of libspearmint_b200.so (see include/spearmint_b200.h).
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -93,8 +94,8 @@ size_t potrf_ll_workspace_bytes(int, int);
 template <typename T>
 int sobol_generate(int, long, long, const uint32_t*, T*, cudaStream_t);
 size_t tc_guard_workspace_bytes(int, int);
-int tc_guard(int, int, int, int, const float*, const float*, const float*, const float*, const float*, float*, void*, size_t,
-             cudaStream_t);
+int tc_guard(int, int, int, int, const float*, const float*, const float*, const float*, const float*, const int*, float*, void*,
+             size_t, cudaStream_t);
 int potrf_ll_f64(int, int, double*, double*, int*, int, cudaStream_t);
 
 }  // namespace smk
@@ -224,8 +225,9 @@ int smk_sobol_generate_f64(int D, long long n, long long skip, const uint32_t* V
 }
 size_t smk_tc_guard_workspace_bytes(int Np, int S) { return tc_guard_workspace_bytes(Np, S); }
 int smk_tc_guard_f32(int N, int Npad, int Np, int S, const float* L, const float* linv_hi, const float* linv_lo,
-                     const float* amp2, const float* noise, float* g, void* workspace, size_t workspace_bytes, void* stream) {
-  return tc_guard(N, Npad, Np, S, L, linv_hi, linv_lo, amp2, noise, g, workspace, workspace_bytes, ST(stream));
+                     const float* amp2, const float* noise, const int* rows, float* g, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  return tc_guard(N, Npad, Np, S, L, linv_hi, linv_lo, amp2, noise, rows, g, workspace, workspace_bytes, ST(stream));
 }
 int smk_debug_kxt_tc_timeline(long long* out, int n) { return kxt_tc_timeline(out, n); }
 size_t smk_kxt_pack_workspace_bytes(int Np, int M, int S) { return kxt_pack_workspace_bytes(Np, M, S); }
@@ -377,19 +379,33 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
   int rc;
   if ((rc = smk_cov_build_f32(kind, N, N, D, S, dX, nullptr, dil, da, dn, fac, Npad, st))) return rc;
   if ((rc = smk_potrf_lower_batched_f32(Npad, S, fac, winv, info, st))) return rc;
-  // tensor-core path: explicit inverse (split), alpha by two mat-vecs, fp16 operand pack, tcgen05 3xFP16 predict
-  float* lhi = linv;
-  float* llo = linv + (size_t)S * Np * Np;
-  float* tmp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws2) + smk_trtri_workspace_bytes(Np, S));
-  if ((rc = smk_trtri_split_f32(Npad, Np, S, fac, winv, lhi, llo, ws2, smk_trtri_workspace_bytes(Np, S), st))) return rc;
-  if ((rc = smk_linv_alpha_f32(N, Np, S, lhi, llo, dy, dm, alpha, Npad, tmp, st))) return rc;
-  void* lh16 = l16;
-  void* ll16 = l16 + (size_t)S * Np * Np * sizeof(__half);
-  int* lexp = reinterpret_cast<int*>(l16 + 2 * (size_t)S * Np * Np * sizeof(__half));
-  if ((rc = smk_linv_pack_f16(Np, S, lhi, llo, lh16, ll16, lexp, st))) return rc;
-  if ((rc = smk_predict_tc_f32(kind, N, Np, M, D, S, dX, dC, dil, da, dm, lh16, ll16, lexp, alpha, Npad, mv,
-                               mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, st)))
-    return rc;
+  // Factors of fewer than SMK_TC_MIN_N (default 2048) observations take the blocked-substitution chain (3-8x more accurate
+  // on the smooth, ill-conditioned problems small N goes with), larger ones the tensor-core chain:
+  // explicit inverse (split), alpha by two mat-vecs, fp16 operand pack, tcgen05 3xFP16 predict.
+  int tc_min_n = 2048;
+  { const char* e = getenv("SMK_TC_MIN_N"); if (e && e[0]) tc_min_n = atoi(e); }
+  if (N < tc_min_n) {
+    const size_t pwb = smk_predict_workspace_bytes(4, Npad);
+    void* pws = g_ws.get(pwb > wsb ? pwb : wsb);
+    if (!pws) { snprintf(g_err, sizeof(g_err), "cudaMalloc failed"); return SMK_ERR_CUDA; }
+    if ((rc = smk_chol_solve_f32(N, Npad, S, 1, fac, winv, dy, 0, N, dm, alpha, nullptr, nullptr, st))) return rc;
+    if ((rc = smk_predict_f32(kind, N, Npad, M, D, S, dX, dC, dil, da, dm, fac, winv, alpha, mv, mv + (size_t)S * ldm, ldm,
+                              pws, pwb, st)))
+      return rc;
+  } else {
+    float* lhi = linv;
+    float* llo = linv + (size_t)S * Np * Np;
+    float* tmp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws2) + smk_trtri_workspace_bytes(Np, S));
+    if ((rc = smk_trtri_split_f32(Npad, Np, S, fac, winv, lhi, llo, ws2, smk_trtri_workspace_bytes(Np, S), st))) return rc;
+    if ((rc = smk_linv_alpha_f32(N, Np, S, lhi, llo, dy, dm, alpha, Npad, tmp, st))) return rc;
+    void* lh16 = l16;
+    void* ll16 = l16 + (size_t)S * Np * Np * sizeof(__half);
+    int* lexp = reinterpret_cast<int*>(l16 + 2 * (size_t)S * Np * Np * sizeof(__half));
+    if ((rc = smk_linv_pack_f16(Np, S, lhi, llo, lh16, ll16, lexp, st))) return rc;
+    if ((rc = smk_predict_tc_f32(kind, N, Np, M, D, S, dX, dC, dil, da, dm, lh16, ll16, lexp, alpha, Npad, mv,
+                                 mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, st)))
+      return rc;
+  }
   if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, nullptr, st))) return rc;
   std::vector<double> hout((size_t)S * ldm);
   std::vector<int> hinfo(S);

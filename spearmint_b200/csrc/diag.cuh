@@ -343,15 +343,46 @@ __device__ void panel_sub_block(T* __restrict__ Ap, int ld, const T* __restrict_
   T* xt = wt + NP * TILE;                   // panel rows: tile q = columns 32 q .. 32 q + 31
   T* tt = xt + NP * TILE;                   // scratch: A_p - sum
   const int tid = threadIdx.x;
-  // ---- loads (coalesced 32-element row segments)
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, k = e % NB, bi = i >> 5, bk = k >> 5;
-    if (bk < bi) lt[(bi * (bi - 1) / 2 + bk) * TILE + (i & 31) * LDT + (k & 31)] = Ljj[(long)i * ld + k];
-  }
-  for (int e = tid; e < NP * SB * SB; e += 256) wt[(e / (SB * SB)) * TILE + ((e / SB) % SB) * LDT + (e % SB)] = wd[e];
-  for (int e = tid; e < SB * NB; e += 256) {
-    const int i = e / NB, k = e % NB;
-    xt[(k >> 5) * TILE + i * LDT + (k & 31)] = Ap[(long)i * ld + k];
+  // ---- loads: every thread issues all of its global reads before the first shared-memory store (this kernel sits on the
+  //      spine: a load loop with one request in flight per thread cost 17 of its 20 us)
+  {
+    constexpr int NLV = PS::NL * 4, NWV = NP * 4, NXV = NB / 8;       // values per thread: L tiles, W tiles, panel rows
+    T lv[NLV > 0 ? NLV : 1], wv[NWV], xv[NXV];
+#pragma unroll
+    for (int t = 0; t < PS::NL; ++t) {
+      int bi = 1;
+      while (bi * (bi + 1) / 2 <= t) ++bi;                              // tile t = (bi, bk), bk < bi
+      const int bk = t - bi * (bi - 1) / 2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * 256;
+        lv[t * 4 + q] = Ljj[(long)(bi * SB + (e >> 5)) * ld + bk * SB + (e & 31)];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NWV; ++q) wv[q] = wd[tid + q * 256];
+#pragma unroll
+    for (int q = 0; q < NXV; ++q) {
+      const int e = tid + q * 256;
+      xv[q] = Ap[(long)(e / NB) * ld + (e % NB)];
+    }
+#pragma unroll
+    for (int t = 0; t < PS::NL; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * 256;
+        lt[t * TILE + (e >> 5) * LDT + (e & 31)] = lv[t * 4 + q];
+      }
+#pragma unroll
+    for (int q = 0; q < NWV; ++q) {
+      const int e = tid + q * 256;
+      wt[(e >> 10) * TILE + ((e >> 5) & 31) * LDT + (e & 31)] = wv[q];
+    }
+#pragma unroll
+    for (int q = 0; q < NXV; ++q) {
+      const int e = tid + q * 256, i = e / NB, k = e % NB;
+      xt[(k >> 5) * TILE + i * LDT + (k & 31)] = xv[q];
+    }
   }
   __syncthreads();
   BlkAcc<T> acc;

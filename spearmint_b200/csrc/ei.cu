@@ -5,8 +5,8 @@
 //     optionally divided by exp(predicted log-duration).
 // One thread per candidate, samples in the inner loop: every load is a fully coalesced 128-byte warp
 // row of mu[s][f][:] / var[s][:], the kernel is a pure HBM sweep (8 bytes in + 4 out per pair without
-// fantasies).  EI itself is evaluated in double: u*Phi(u) + phi(u) cancels catastrophically for u << 0
-// and the chooser ranks candidates by exactly those tail values late in an optimisation run.
+// fantasies).  EI is STORED in double and evaluated in double wherever float32 would not do: u*Phi(u) + phi(u) cancels
+// catastrophically for u << 0 and the chooser ranks candidates by exactly those tail values late in a run (ei_one_f32).
 //
 // Selection (reference OPT:270-271 argsort(mean)[-k:], OPT:294 argmax(mean)): two-stage top-k.
 #include "common.cuh"
@@ -22,16 +22,35 @@ __device__ __forceinline__ double ei_one(double best, double m, double v) {
   return s * (u * cdf + pdf);
 }
 
+// float32 moments (the grid path): the expression is evaluated in float32 wherever that is exact enough -- u > -4, where
+// u Phi(u) + phi(u) cancels by less than a factor 20 and erfcf / expf keep the result within ~5e-6 relative of the double
+// value (the moments themselves carry 1e-4) -- and in double in the tail, where the chooser ranks candidates by values
+// that float32 would flush to zero.  This is what makes the sweep an HBM sweep (12-16 bytes per pair against ~45
+// float32 instructions) instead of an fp64-ALU loop (profiles/r02_ei_sweep_bandwidth.md).  The result is a double either way.
+__device__ __forceinline__ double ei_one(double best, float m, float v) { return ei_one(best, (double)m, (double)v); }
+__device__ __forceinline__ double ei_one_f32(float best, float m, float v) {
+  if (v > 0.f) {
+    const float s = sqrtf(v);
+    const float u = (best - m) / s;
+    if (u > -4.0f) {
+      const float cdf = 0.5f * erfcf(-u * 0.70710678f);
+      const float pdf = 0.39894228f * expf(-0.5f * u * u);
+      return (double)(s * fmaf(u, cdf, pdf));
+    }
+  }
+  return ei_one((double)best, (double)m, (double)v);
+}
+__device__ __forceinline__ double ei_fast(float best, float m, float v) { return ei_one_f32(best, m, v); }
+__device__ __forceinline__ double ei_fast(double best, double m, double v) { return ei_one(best, m, v); }
 
 // EI of candidate j under sample s (mean over the F fantasies, optional division by the predicted duration)
 template <typename T>
 __device__ __forceinline__ double ei_cand(int F, const T* mu, const T* var, int ldm, const T* best, const T* log_time, int s,
                                           int j) {
-  const double v = (double)var[(long)s * ldm + j];
   const T* mrow = mu + (long)s * F * ldm + j;
   const T* brow = best + (long)s * F;
   double acc = 0.0;
-  for (int f = 0; f < F; ++f) acc += ei_one((double)brow[f], (double)mrow[(long)f * ldm], v);
+  for (int f = 0; f < F; ++f) acc += ei_fast(brow[f], mrow[(long)f * ldm], var[(long)s * ldm + j]);
   double e = (F > 1) ? acc / (double)F : acc;
   if (log_time) e /= exp((double)log_time[(long)s * ldm + j]);
   return e;
@@ -87,21 +106,20 @@ __global__ void __launch_bounds__(256) ei_sweep_kernel(int M, int S, int F, cons
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        double e = ei_one((double)best[s + q], (double)m[q], (double)v[q]);
+        double e = ei_fast(best[s + q], m[q], v[q]);
         if (log_time) e /= exp((double)lt[q]);
         if (ei) ei[(long)(s + q) * ldm + j] = e;
         total += e;
       }
     }
     for (; s < S; ++s) {
-      double e = ei_one((double)best[s], (double)mu[(long)s * ldm + j], (double)var[(long)s * ldm + j]);
+      double e = ei_fast(best[s], mu[(long)s * ldm + j], var[(long)s * ldm + j]);
       if (log_time) e /= exp((double)log_time[(long)s * ldm + j]);
       if (ei) ei[(long)s * ldm + j] = e;
       total += e;
     }
   } else {
     for (int s = 0; s < S; ++s) {
-      const double v = (double)var[(long)s * ldm + j];
       const T* mrow = mu + (long)s * F * ldm + j;
       const T* brow = best + (long)s * F;
       double acc = 0.0;
@@ -111,9 +129,9 @@ __global__ void __launch_bounds__(256) ei_sweep_kernel(int M, int S, int F, cons
 #pragma unroll
         for (int q = 0; q < 4; ++q) m[q] = mrow[(long)(f + q) * ldm];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc += ei_one((double)brow[f + q], (double)m[q], v);
+        for (int q = 0; q < 4; ++q) acc += ei_fast(brow[f + q], m[q], var[(long)s * ldm + j]);
       }
-      for (; f < F; ++f) acc += ei_one((double)brow[f], (double)mrow[(long)f * ldm], v);
+      for (; f < F; ++f) acc += ei_fast(brow[f], mrow[(long)f * ldm], var[(long)s * ldm + j]);
       double e = acc / (double)F;
       if (log_time) e /= exp((double)log_time[(long)s * ldm + j]);
       if (ei) ei[(long)s * ldm + j] = e;

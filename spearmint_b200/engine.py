@@ -58,8 +58,9 @@ class HyperBatch(object):
 class Factor(object):
     """Batched Cholesky factors of K_s = amp2_s (k + 1e-6 I) + noise_s I for S hyper-samples."""
 
-    def __init__(self, eng, kind, X, hb, L=None, winv=None, info=None):
+    def __init__(self, eng, kind, X, hb, L=None, winv=None, info=None, factor_impl=None):
         self.eng, self.kind, self.hb = eng, kind, hb
+        self.factor_impl = factor_impl or eng.factor_impl
         self.X = X
         self.N, self.D = X.shape
         self.Npad = _ceil(self.N, 128)
@@ -72,7 +73,7 @@ class Factor(object):
         st = eng.stream()
         check(fn("smk_cov_build", dt)(KINDS[kind], self.N, self.N, self.D, S, ptr(X), None, ptr(hb.inv_ls),
                                       ptr(hb.amp2), ptr(hb.noise), ptr(self.L), self.Npad, st), "cov_build")
-        if eng.factor_impl == "tc" and dt == torch.float32 and self.Npad >= 256:
+        if self.factor_impl == "tc" and dt == torch.float32 and self.Npad >= 256:
             nb = 2 * S * self.Npad * self.Npad * 4
             ws = eng.take((nb,), torch.uint8)
             eng.give(ws)                      # scratch of this call only (stream-ordered reuse)
@@ -101,7 +102,7 @@ class Factor(object):
             Np = L.smk_tc_np(self.N)
             hi = self._take((S, Np, Np), torch.float32)
             lo = self._take((S, Np, Np), torch.float32)
-            if eng.factor_impl == "tc" and self.Npad >= 256:
+            if self.factor_impl == "tc" and self.Npad >= 256:
                 nb = L.smk_trtri_tc_workspace_bytes(self.Npad, Np, S)
                 ws = eng.take((nb,), torch.uint8)
                 eng.give(ws)
@@ -142,18 +143,19 @@ class Factor(object):
                                    ptr(tmp), eng.stream()), "linv_alpha")
         return alpha
 
-    def guard(self):
-        """[S] float32 on the device: estimated relative error of the predictive variance at a candidate sitting on an
-        observed point if the explicit inverse is used (csrc/guard.cu)."""
+    def guard(self, rows):
+        """[S] float32 on the device: estimated relative error of the predictive variance at a candidate sitting on one of
+        the observed points ``rows`` (4 indices: the incumbents) if the explicit inverse is used (csrc/guard.cu)."""
         eng, L = self.eng, _lib.lib()
         hi, lo, Np = self.linv()
         S = self.hb.S
         g = torch.empty((S,), dtype=torch.float32, device=eng.device)
+        rows = torch.as_tensor(np.resize(np.asarray(rows, dtype=np.int32), 4), device=eng.device)
         nb = L.smk_tc_guard_workspace_bytes(Np, S)
         ws = eng.take((nb,), torch.uint8)
         eng.give(ws)
         check(L.smk_tc_guard_f32(self.N, self.Npad, Np, S, ptr(self.L), ptr(hi), ptr(lo), ptr(self.hb.amp2),
-                                 ptr(self.hb.noise), ptr(g), ptr(ws), nb, eng.stream()), "tc_guard")
+                                 ptr(self.hb.noise), ptr(rows), ptr(g), ptr(ws), nb, eng.stream()), "tc_guard")
         return g
 
     def check_pd(self):
@@ -219,9 +221,16 @@ class GPEIEngine(object):
             self.predict_impl = "simt"
         # N^3 steps (Cholesky trailing update, triangular inverse): "tc" = tcgen05 3xTF32 left-looking variants
         self.factor_impl = os.environ.get("SMK_FACTOR_IMPL", "tc" if self.predict_impl == "tc" else "simt")
-        # accuracy guard of the explicit-inverse (tensor-core) predict (csrc/guard.cu, _guarded_impl): a hyper-sample whose
-        # estimated EI error exceeds this fraction of its largest EI is re-evaluated in float64 (0 disables the guard)
-        self.guard_threshold = float(os.environ.get("SMK_TC_GUARD", "1.5e-3"))
+        # The explicit-inverse tensor-core chain is the path for LARGE factors.  Below tc_min_n observations the float32
+        # blocked-substitution chain (SIMT Cholesky + SIMT predict) is used: it is 3-8x more accurate on the smooth,
+        # ill-conditioned problems small N goes with (C2 / C4: 1.5e-3 against 8e-3 ... 1.2e-2 of max EI)
+        # and at that size it costs milliseconds.
+        self.tc_min_n = int(os.environ.get("SMK_TC_MIN_N", "2048"))
+        # opt-in accuracy guard of the tensor-core chain (csrc/guard.cu, _guarded_impl): a hyper-sample whose ESTIMATED EI
+        # error exceeds this fraction of its EI scale is re-evaluated in float64.  The estimate is conservative (it
+        # over-predicts the measured error by up to 8x), so it is off by default (0) and meant for users whose problems are
+        # both large and badly conditioned.
+        self.guard_threshold = float(os.environ.get("SMK_TC_GUARD", "0"))
         self.last = {}
         self.last_guard = None
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
@@ -322,6 +331,12 @@ class GPEIEngine(object):
 
     def factor(self, kind, X, hb, **kw):
         return Factor(self, kind, X, hb, **kw)
+
+    def chain_for(self, n):
+        """("tc" | "simt") for a factor of n observations: the tensor-core chain from tc_min_n on, else blocked substitution."""
+        if self.predict_impl == "tc" and self.dtype == torch.float32 and n >= self.tc_min_n:
+            return "tc"
+        return "simt"
 
     def cov(self, kind, hb, X, Y=None):
         """Batched chooser.cov (OPT:207-212): returns [S][N][N] (self, jitter included, no noise) or [S][N][M]."""
@@ -446,10 +461,11 @@ class GPEIEngine(object):
             p.time = (tfac, ta)
         if P == 0:
             t = self._t0()
-            fac = self.factor(kind, Xo, hb)
+            chain = self.chain_for(Xo.shape[0])
+            fac = self.factor(kind, Xo, hb, factor_impl=chain if self.factor_impl == "tc" else "simt")
             self._t1("cov_potrf", t)
             t = self._t0()
-            p.impl = self._guarded_impl(fac, p)
+            p.impl = self._guarded_impl(fac, p) if chain == "tc" else "simt"
             if p.impl == "tc":
                 alpha = fac.alpha_via_linv(yd)       # explicit inverse (trtri, once per factor batch) + two mat-vecs
             else:
@@ -476,10 +492,13 @@ class GPEIEngine(object):
         engine.  Well-conditioned problems (the headline: bound / max EI ~ 6e-4) never trip it; smooth low-dimensional ones
         (C2, C4: ~5e-3) do.  Measured against actual errors in profiles/r02_precision_guard.md."""
         p.gbound, p.flagged, p.prep64 = None, None, None
-        if self.predict_impl != "tc" or self.dtype != torch.float32:
-            return self.predict_impl
         if self.guard_threshold > 0:
-            g = fac.guard().double().cpu().numpy()                       # one small read per factor batch
+            # probes: the observed points with the lowest values -- the incumbent (the chooser's jitter cloud sits on it) and
+            # its runners-up, where EI concentrates
+            vals = p.host.get("vals")
+            rows = np.argsort(vals)[:4] if vals is not None else [fac.N - 1]
+            rows = [int(r) for r in rows if r < fac.N]
+            g = fac.guard(rows).double().cpu().numpy()                   # one small read per factor batch
             hb = fac.hb
             p.gbound = 0.2 * g * np.sqrt(hb.host_noise + JITTER * hb.host_amp2)
             self.last_guard = dict(g_max=float(g.max()), bound_max=float(p.gbound.max()))
@@ -519,16 +538,18 @@ class GPEIEngine(object):
             fant[s, :, :N] = vals[None, :]
             fant[s, :, N:] = pf.T
             bests[s] = np.minimum(vals.min(), pf.min(axis=0))                     # OPT:597
+        chain = self.chain_for(N + P)
         if h64 is self:
             fac = fac64
         else:
             del fac64
-            fac = self.factor(kind, torch.cat([Xo, Pd], dim=0).contiguous(), hb)
+            fac = self.factor(kind, torch.cat([Xo, Pd], dim=0).contiguous(), hb,
+                              factor_impl=chain if self.factor_impl == "tc" else "simt")
             fac.check_pd()
         fant_d = self.to_dev(fant)                                                # [S][F][N+P]
         alpha_f, _, _ = fac.solve(fant_d, F=F, y_stride=F * (N + P), ldy=N + P)   # OPT:603
         p.fac, p.alpha, p.F = fac, alpha_f, F
-        p.impl = self._guarded_impl(fac, p)
+        p.impl = self._guarded_impl(fac, p) if chain == "tc" else "simt"
         p.bests, p.bests_host = self.to_dev(bests), bests
         p.pred_alpha = torch.zeros((S, fac.Npad), dtype=self.dtype, device=self.device)
 
@@ -566,10 +587,16 @@ class GPEIEngine(object):
         ei, _ = self.ei_sweep(M, hb.S, p.F, mu, var, ldm, p.bests, log_time, True, None, ei_max=ei_max, accumulate=False)
         self._t1("ei_sweep", t)
         if p.flagged is None:                                             # decided on the first sweep of this factor batch
-            mx = ei_max.cpu().numpy().view(np.float64)
-            p.flagged = [int(s) for s in np.nonzero(p.gbound > self.guard_threshold * mx)[0]]
-            self.last_guard = dict(self.last_guard or {}, flagged=len(p.flagged), S=hb.S,
-                                   worst_ratio=float(np.max(p.gbound / np.maximum(mx, 1e-300))))
+            # scale of each sample's EI: its own maximum, but not below the largest MEAN EI of the batch -- a sample whose EI
+            # is negligible everywhere cannot move the proposal and is not worth a float64 pass
+            tmp = torch.zeros((ldm,), dtype=torch.float64, device=self.device)
+            check(_lib.lib().smk_ei_colsum(M, hb.S, ptr(ei), ldm, ptr(tmp), self.stream()), "ei_colsum")
+            _, top = self._topk_once(tmp, M, 1)
+            both = torch.cat([ei_max.view(torch.float64), top / float(hb.S)]).cpu().numpy()   # the one host read
+            scale = np.maximum(both[:hb.S], both[hb.S])
+            ratio = p.gbound / np.maximum(scale, 1e-300)
+            p.flagged = [int(s) for s in np.nonzero(ratio > self.guard_threshold)[0]]
+            self.last_guard = dict(self.last_guard or {}, flagged=len(p.flagged), S=hb.S, worst_ratio=float(ratio.max()))
         if p.flagged:
             self._reevaluate_f64(p, Cd, cand_host, ei)
         check(_lib.lib().smk_ei_colsum(M, hb.S, ptr(ei), ldm, ptr(ei_sum), self.stream()), "ei_colsum")
@@ -697,6 +724,10 @@ class LogLik(object):
         if max_batch is None:      # one slice move = 3 + SPECULATE points (util.py); small N is pure launch latency
             max_batch = 8 if self.N <= 1024 else 6
         self.max_batch = max_batch
+        # slice-sampler speculation (util._slice_along): small matrices are pure launch latency -- evaluate everything a move
+        # may need at once; from N ~ 1500 on a batch costs what its flops cost, so only the always-needed points go first
+        # and shrink proposals follow in pairs once the interval is final
+        self.speculate = (3, 0) if self.N <= 1536 else (0, 2)
         dt, dev = eng.dtype, eng.device
         self.L = torch.empty((max_batch, self.Npad, self.Npad), dtype=dt, device=dev)
         # float64: dedicated look-ahead / DMMA factorisation (csrc/potrf_ll.cu); its workspace holds the inverse diagonal

@@ -22,32 +22,45 @@ def unpack_args(arg_string):
 SPECULATE = 3    # shrink proposals evaluated ahead of time when the log-probability supports batching
 
 
+def _peek_shrink(lower, upper, n):
+    """The next n shrink proposals of the interval (lower, upper) assuming each one is rejected, obtained by PEEKING the
+    global RNG (state saved and restored): the draws consumed later are exactly these."""
+    state = npr.get_state()
+    peek = npr.rand(n)
+    npr.set_state(state)
+    zs, lo, hi = [], lower, upper
+    for r in peek:
+        z = (hi - lo) * r + lo
+        zs.append(z)
+        if z < 0:
+            lo = z
+        elif z > 0:
+            hi = z
+    return zs
+
+
 def _slice_along(direction, x0, logprob, sigma, step_out, max_steps_out):
     """One slice-sampling move along ``direction`` (reference util.py:36-75).  RNG call order:
     rand (interval placement), rand (slice height), then one rand per shrink proposal.
 
-    If ``logprob`` has a ``prefetch(points)`` method (spearmint_b200's GPU log-likelihood), the points this move
-    will most likely visit -- 0, lower, upper and the first shrink proposals assuming no step-out -- are handed to it
-    first so they are evaluated as ONE batch.  The proposals are obtained by PEEKING the global RNG (state saved and
-    restored), so the draws consumed, the points visited and therefore the chain are exactly the reference's."""
+    If ``logprob`` has a ``prefetch(points)`` method (spearmint_b200's GPU log-likelihood), the points this move will
+    most likely visit are handed to it first so that they are evaluated as ONE batched factorisation:
+      phase 1: 0, lower, upper (always needed) and the first ``speculate[0]`` shrink proposals assuming no step-out;
+      phase 2: once the interval is final, shrink proposals in groups of ``speculate[1]``.
+    ``logprob.speculate`` = (s1, s2) tunes this to the cost model of the likelihood: a latency-bound factorisation
+    (small N) evaluates 6 points for the price of one, a flop-bound one (N = 4096) pays for every wasted point.
+    The proposals are obtained by PEEKING the global RNG, so the draws consumed, the points visited and therefore the
+    chain are exactly the reference's."""
     def lp(z):
         return logprob(direction * z + x0)
 
     upper = sigma * npr.rand()
     lower = upper - sigma
     u_height = npr.rand()
-    if hasattr(logprob, "prefetch"):
-        state = npr.get_state()
-        peek = npr.rand(SPECULATE)
-        npr.set_state(state)
-        zs, lo, hi = [0.0, lower, upper], lower, upper
-        for r in peek:
-            z = (hi - lo) * r + lo
-            zs.append(z)
-            if z < 0:
-                lo = z
-            elif z > 0:
-                hi = z
+    can_prefetch = hasattr(logprob, "prefetch")
+    s1, s2 = getattr(logprob, "speculate", (SPECULATE, 0)) if can_prefetch else (0, 0)
+    if can_prefetch:
+        zs = [0.0, lower, upper] + _peek_shrink(lower, upper, s1)
         logprob.prefetch([direction * z + x0 for z in zs])
     height = np.log(u_height) + lp(0.0)
     n_lo = n_hi = 0
@@ -58,9 +71,15 @@ def _slice_along(direction, x0, logprob, sigma, step_out, max_steps_out):
         while lp(upper) > height and n_hi < max_steps_out:
             n_hi += 1
             upper += sigma
+    covered = s1 if (n_lo == 0 and n_hi == 0) else 0      # proposals of phase 1 still valid (the interval did not move)
+    it = 0
     while True:
+        if can_prefetch and s2 > 0 and it >= covered:
+            logprob.prefetch([direction * z + x0 for z in _peek_shrink(lower, upper, s2)])
+            covered = it + s2
         z = (upper - lower) * npr.rand() + lower
         val = lp(z)
+        it += 1
         if np.isnan(val):
             raise Exception("Slice sampler got a NaN")
         if val > height:
@@ -103,6 +122,7 @@ class CachedLogProb(object):
     def __init__(self, loglik, hypers_of):
         self.ll, self.hypers_of = loglik, hypers_of
         self.cache = {}
+        self.speculate = getattr(loglik, "speculate", (SPECULATE, 0))    # (phase 1, phase 2) depth, see _slice_along
 
     @staticmethod
     def _key(x):

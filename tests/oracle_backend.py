@@ -12,10 +12,11 @@ class _State(object):
 class OracleBackend(object):
     name = "oracle"
 
-    def __init__(self, batched=False):
+    def __init__(self, batched=False, speculate=None):
         self.loglik_calls = 0
         self.batches = 0
         self.batched = batched
+        self.speculate = speculate
 
     def loglik(self, kind, comp, vals):
         outer = self
@@ -27,6 +28,8 @@ class OracleBackend(object):
             return ll
 
         class Batched(object):          # same interface as engine.LogLik: exercises the speculative sampler path
+            if outer.speculate:
+                speculate = outer.speculate
             def __call__(self, mean, noise, amp2, ls):
                 return ll(mean, noise, amp2, ls)
 

@@ -159,20 +159,24 @@ def test_speculative_batched_sampler_keeps_the_chain(name, tmp_path):
     same hyper-samples, same proposal, same final RNG state as the sequential path, with far fewer sequential calls."""
     g = load(name)
     outs = []
-    for batched in (False, True):
-        d = tmp_path / ("b%d" % batched)
+    # False: sequential; (3, 0): everything speculated up front (latency-bound sizes); (0, 2), (1, 3): the two-phase
+    # schedule of flop-bound sizes (interval ends first, shrink proposals in small groups afterwards)
+    for i, batched in enumerate((False, (3, 0), (0, 2), (1, 3))):
+        d = tmp_path / ("b%d" % i)
         d.mkdir()
         ch = _make(g, d)
-        ch._backend = OracleBackend(batched=batched)
+        ch._backend = OracleBackend(batched=bool(batched), speculate=batched or None)
         np.random.seed(int(g["seed"]))
         ret = ch.next(g["grid"], g["values"], g["durations"], g["candidates"], g["pending"], g["complete"])
         outs.append((ch.hyper_samples, ret, np.random.rand(), ch._backend))
-    (hs0, r0, u0, b0), (hs1, r1, u1, b1) = outs
-    for a, b in zip(hs0, hs1):
-        np.testing.assert_array_equal(np.hstack(a), np.hstack(b))
-    assert u0 == u1
-    assert (r0[0], tuple(r0[1])) == (r1[0], tuple(r1[1])) if isinstance(r0, tuple) else r0 == r1
-    assert b1.batches < 0.5 * b0.loglik_calls          # sequential depth at least halved
+    hs0, r0, u0, b0 = outs[0]
+    for hs1, r1, u1, b1 in outs[1:]:
+        for a, b in zip(hs0, hs1):
+            np.testing.assert_array_equal(np.hstack(a), np.hstack(b))
+        assert u0 == u1
+        assert (r0[0], tuple(r0[1])) == (r1[0], tuple(r1[1])) if isinstance(r0, tuple) else r0 == r1
+    assert outs[1][3].batches < 0.5 * b0.loglik_calls          # sequential depth at least halved
+    assert outs[2][3].loglik_calls < outs[1][3].loglik_calls   # the two-phase schedule wastes fewer evaluations
 
 
 @pytest.mark.parametrize("name", ["mll_d3_m52", "mll_d5_ardse", "mll_d2_m32"])

@@ -38,17 +38,19 @@ def _check(ei, ref, prec):
 @pytest.mark.parametrize("name", OPT_CASES)
 @pytest.mark.parametrize("prec", ["f64", "f32", "f32-simt"])
 def test_ei_over_hypers_vs_reference(engines, name, prec):
-    """f32 = production path (tcgen05 3xTF32 predict); f32-simt = the register-tiled FMA predict; f64 = logic check."""
+    """f32 = the tensor-core chain (tcgen05 Cholesky / inverse / 3xFP16 predict, forced: these factors are small);
+    f32-simt = what the engine picks for them by default (blocked substitution); f64 = logic check."""
     g = load(name)
     comp, pend, cand, vals = sets(g)
     eng = engines[prec.split("-")[0]]
-    saved = eng.predict_impl
-    if prec == "f32-simt":
-        eng.predict_impl = "simt"
+    saved = getattr(eng, "tc_min_n", None)
+    if prec == "f32":
+        eng.tc_min_n = 0
     try:
         ei = eng.ei_over_hypers(str(g["kind"]), hypers(g), comp, pend, cand, vals, g["normals"])
     finally:
-        eng.predict_impl = saved
+        if saved is not None:
+            eng.tc_min_n = saved
     _check(ei, g["overall_ei"], prec.split("-")[0])
 
 
@@ -103,7 +105,12 @@ def test_ei_path_medium_n_vs_oracle(engines, D, N, M):
     ref = O.ei_over_hypers("Matern52", hs, comp, pend, cand, vals)
     eng = engines["f32"]
     assert eng.predict_impl == "tc" and eng.factor_impl == "tc"
-    ei = eng.ei_over_hypers("Matern52", hs, comp, pend, cand, vals)
+    saved = eng.tc_min_n
+    eng.tc_min_n = 0                # the engine would route factors this small to the substitution chain: force the TC chain
+    try:
+        ei = eng.ei_over_hypers("Matern52", hs, comp, pend, cand, vals)
+    finally:
+        eng.tc_min_n = saved
     assert np.all(np.isfinite(ei))
     for s in range(ref.shape[1]):
         r, e = ref[:, s], ei[:, s]
@@ -155,3 +162,25 @@ def test_topk_beyond_256(engines):
     ref = np.lexsort((-np.arange(5000), score))[-700:]
     assert np.array_equal(idx.cpu().numpy(), ref)
     assert np.array_equal(val.cpu().numpy(), score[ref])
+
+
+def test_accuracy_guard_reevaluates_in_float64(engines):
+    """The opt-in guard of the tensor-core chain (SMK_TC_GUARD): with a threshold every hyper-sample exceeds, the engine
+    re-evaluates all of them on the float64 build and the result is the reference's to float64 accuracy."""
+    from oracle import gp_oracle as O
+    rs = np.random.RandomState(12)
+    D, N, M = 6, 300, 500
+    comp, cand = rs.rand(N, D), rs.rand(M, D)
+    y = np.sin(3 * comp).sum(1)
+    vals = (y - y.mean()) / y.std()
+    hs = [(0.0, 1e-3, 1.0, rs.uniform(0.5, 1.5, D)) for _ in range(3)]
+    pend = np.zeros((0, D))
+    eng = engines["f32"]
+    saved = (eng.tc_min_n, eng.guard_threshold)
+    eng.tc_min_n, eng.guard_threshold = 0, 1e-12
+    try:
+        ei = eng.ei_over_hypers("Matern52", hs, comp, pend, cand, vals)
+    finally:
+        eng.tc_min_n, eng.guard_threshold = saved
+    assert eng.last_guard["flagged"] == 3
+    _check(ei, O.ei_over_hypers("Matern52", hs, comp, pend, cand, vals), "f64")

@@ -175,9 +175,16 @@ def test_ei_sweep(engines, F):
             e = O._ei_from_moments(best[s].astype(float)[None, :], mu[s, :, :M].astype(float).T, sdev).mean(axis=1)
             ref[s] = e / (np.exp(log_time[s, :M].astype(float)) if log_time is not None else 1.0)
         got = ei.double().cpu().numpy()[:, :M]
-        # double evaluation, double storage; u*Phi(u)+phi(u) amplifies 1-ulp erfc/FMA differences by ~u^2 in the tail
-        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-300)
-        np.testing.assert_allclose(ei_sum.double().cpu().numpy()[:M], ref.sum(0), rtol=1e-9, atol=1e-300)
+        # double storage.  float32 moments are evaluated in float32 where u > -4 (cancellation < 20x: ~1e-5 relative) and in
+        # double in the tail (u*Phi(u)+phi(u) amplifies 1-ulp erfc/FMA differences by ~u^2 there): the deep-tail entries
+        # [0, :10] must be double-exact, everything else float32-exact
+        np.testing.assert_allclose(got, ref, rtol=4e-5, atol=1e-300)
+        np.testing.assert_allclose(got[0, :10], ref[0, :10], rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(ei_sum.double().cpu().numpy()[:M], ref.sum(0), rtol=4e-5, atol=1e-300)
+        e64, _ = engines["f64"].ei_sweep(M, S, F, torch.from_numpy(mu).double().cuda(), torch.from_numpy(var).double().cuda(),
+                                         ldm, torch.from_numpy(best).double().cuda(),
+                                         None if log_time is None else torch.from_numpy(log_time).double().cuda())
+        np.testing.assert_allclose(e64.cpu().numpy()[:, :M], ref, rtol=1e-9, atol=1e-300)
 
 
 @pytest.mark.parametrize("M,k", [(10, 3), (5000, 20), (100000, 20), (4097, 1)])

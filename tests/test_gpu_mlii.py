@@ -58,5 +58,14 @@ def test_gpei_chooser_ml2_next(backend, name, tmp_path):
     ch._backend = backend
     np.random.seed(5)
     ret = ch.next(g["grid"], g["values"], None, g["candidates"], np.array([], dtype=int), g["complete"])
-    assert ret == int(g["next_index"])
     np.testing.assert_allclose(np.hstack([ch.mean, ch.noise, ch.amp2, ch.ls]), g["next_hypers"], rtol=1e-5)
+    if ret != int(g["next_index"]):
+        # ML-II can collapse the length scales (mll_d5_ardse: ls ~ 0.03 in 5-D): K is then diagonal to rounding, every
+        # candidate away from the data has the same EI to ~1e-10 relative and the reference's argmax is decided by float64
+        # round-off.  Such an exact tie may be broken differently; anything else may not.
+        from oracle import gp_oracle as O
+        comp, vals = g["grid"][g["complete"]], g["values"][g["complete"]]
+        h = (ch.mean, ch.noise, ch.amp2, ch.ls)
+        e = O.compute_ei(str(g["kind"]), h, comp, np.zeros((0, comp.shape[1])), g["grid"][g["candidates"]], vals)
+        cand_pos = {int(c): i for i, c in enumerate(g["candidates"])}
+        assert e[cand_pos[ret]] >= e.max() * (1 - 1e-7), (ret, int(g["next_index"]), e[cand_pos[ret]], e.max())

@@ -1,4 +1,5 @@
-"""-m gpu: the PRODUCTION float32 tensor-core path against the float64 oracle at the sizes BASELINE.json quotes.
+"""-m gpu: the PRODUCTION float32 path (tensor-core chain from N = 2048, blocked substitution below) against the float64
+oracle at the sizes BASELINE.json quotes.
 
 The golden fixtures stop at N = 64 and test_gpu_golden.py's oracle cases at N = 1300.  The configurations the bench
 lines are quoted on exercise code paths those sizes never reach (16 row groups, a 32-block Cholesky, several
@@ -32,7 +33,7 @@ def eng():
     import torch
     from spearmint_b200.engine import GPEIEngine
     e = GPEIEngine(dtype=torch.float32)
-    assert e.predict_impl == "tc" and e.factor_impl == "tc"
+    assert e.predict_impl == "tc" and e.factor_impl == "tc" and e.tc_min_n == 2048      # production defaults
     return e
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Achieved HBM bandwidth of the EI sweep kernel (north_star: 'EI scan over candidates as a coalesced HBM sweep').
-Algorithmic bytes per (candidate, sample[, fantasy]) evaluation: read mu (4 B) [+ var 4 B when F == 1] + write ei (4 B / F).
+Algorithmic bytes per (candidate, sample[, fantasy]) evaluation: read mu (4 B) [+ var 4 B when F == 1] + write ei (8 B / F: EI is stored in double).
 The headline grid (M=100k, S=40, F=1) is 48 MB -- launch-latency sized -- so the asymptotic figure is measured on
 larger sweeps (more candidates, and the pending-fantasy shape F=100)."""
 import json
@@ -34,7 +34,7 @@ def run(M, S, F, iters=20):
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
     ms = tot / iters
-    nbytes = 4.0 * M * S * F + 4.0 * M * S + 4.0 * M * S + 8.0 * M      # mu + var + ei + ei_sum (rw)
+    nbytes = 4.0 * M * S * F + 4.0 * M * S + 8.0 * M * S + 16.0 * M     # mu + var + ei (double) + ei_sum (read + write)
     return dict(M=M, S=S, F=F, ms=ms, GBps=nbytes / ms / 1e6, bytes=nbytes)
 
 

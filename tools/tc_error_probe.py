@@ -17,7 +17,7 @@ from spearmint_b200.engine import GPEIEngine, ptr, check, KINDS
 wl, s_idx, M_sub = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 D, N, M, S = bench.WORKLOADS[wl]
 comp, cand, vals, hs = bench.synth(D, N, M, S)
-cand = cand[:M_sub]
+cand = np.vstack([np.random.RandomState(7).randn(10, D) * 0.001 + comp[np.argmin(vals)], cand[:M_sub - 10]])   # jitter cloud first
 h = hs[s_idx]
 mean, noise, amp2, ls = h
 kind = bench.KIND
@@ -83,6 +83,11 @@ rep("GPU beta dump (tensor-core GEMM), float64 square-sum", c - np.sum(beta_dbg 
 rep("GPU var", var_gpu)
 rep("GPU var + GPU mu", var_gpu, mu_gpu)
 rep("exact var + GPU mu", v_ref, mu_gpu)
+print("cloud only (first 10 candidates):")
+for nm, vv, mm in (("GPU var, exact mu", var_gpu, m_ref), ("exact var, GPU mu", v_ref, mu_gpu), ("GPU var + mu", var_gpu, mu_gpu)):
+    ei = O._ei_from_moments(best, mm, np.sqrt(np.maximum(vv, 1e-300)))
+    print("   %-22s cloud max|dEI|/maxEI %.3e   rest %.3e   (EI cloud max %.3e, EI max %.3e)" % (
+        nm, np.abs(ei - ei_ref)[:10].max() / ei_ref.max(), np.abs(ei - ei_ref)[10:].max() / ei_ref.max(), ei_ref[:10].max(), ei_ref.max()))
 d = beta_dbg - b_ab
 print("GEMM error: max|d| %.3e  mean d %+.3e  mean |d| %.3e  ; mean(d*sign(b)) %+.3e (negative = truncation toward zero) ; max|beta| %.3e"
       % (np.abs(d).max(), d.mean(), np.abs(d).mean(), (d * np.sign(b_ab)).mean(), np.abs(b_ab).max()))
