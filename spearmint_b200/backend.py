@@ -69,12 +69,16 @@ class DeviceBackend(object):
             normals = normals[mine]
             st.args = (comp, pend, vals, normals, durs_log)
         chunk = eng.max_samples_per_chunk(_ceil(comp.shape[0] + P, 128), _ceil(200000, 128), F)
-        st.preps = None
+        st.preps, st.pd_checked = None, True
         err = None
         try:
             if st.hs and len(st.hs) <= chunk:        # everything resident: prepare once, sweep many
-                st.preps = eng.prepare(kind, st.hs, comp, pend, vals, normals, st.ths, durs_log)
-                st.preps.fac.check_pd()
+                if eng.can_overlap(comp.shape[0], len(st.hs), P, st.ths):
+                    st.preps = eng.prepare_two_groups(kind, st.hs, comp, vals)   # 2nd half's factor chain on a side stream
+                else:
+                    st.preps = [eng.prepare(kind, st.hs, comp, pend, vals, normals, st.ths, durs_log)]
+                    st.preps[0].fac.check_pd()
+                st.pd_checked = len(st.preps) == 1
         except np.linalg.LinAlgError as e:           # the reference lets spla.cholesky raise; so do we --
             err = e                                  # on every rank, or the others would hang in the all-reduce
         parallel.agree_on_error(err, eng.device)
@@ -89,7 +93,14 @@ class DeviceBackend(object):
         if not st.hs:
             ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=eng.device)
         elif st.preps is not None:
-            ei, ei_sum = eng.ei_prepared(st.preps, eng.to_dev(cand), want_matrix, None, cand_host=cand)
+            ei, ei_sum = eng.ei_groups(st.preps, eng.to_dev(cand), want_matrix, None, cand_host=cand)
+            if not st.pd_checked:                    # deferred until the first sweep is queued: the check synchronises
+                try:
+                    for p in st.preps:
+                        p.fac.check_pd()
+                except np.linalg.LinAlgError as e:
+                    err = e
+                st.pd_checked = True
         else:
             comp, pend, vals, normals, durs_log = st.args
             try:                                     # chunked path: factors are (re)built per pass and may raise here

@@ -56,7 +56,7 @@ constexpr int TBUF = 4;            // TMEM accumulator buffers (4 x 128 columns)
 constexpr int NGRP = 3;            // epilogue groups
 constexpr int MAXD = 32;           // padded dimension limit
 constexpr int MAXK = 96;           // J * Dp limit: one q stage = 128 x 96 halves x (hi, lo) = 48 KB
-constexpr int MAXS = 128;          // one sample per TMEM lane
+constexpr int MAXS = 64;           // samples per launch (one sample per TMEM lane: <= 128; the alpha prefetch holds MAXS / 16 float4 per thread)
 constexpr int THREADS = 16 * 32;
 constexpr int CW = 32;             // columns per epilogue chunk (one tcgen05.ld.x32)
 constexpr int ALD = CW + 4;        // row length (floats) of the staged alpha chunk: 144-byte stride -> conflict-free row reads
@@ -116,6 +116,43 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 
 __device__ __forceinline__ unsigned h2_bits(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
 
+// One 32-column chunk of one accumulator row: distances -> kernel values -> scaled fp16 (hi, lo) into this lane's staging row,
+// running mean.  KIND and EDGE are compile-time: the per-pair kind switch and edge test were ~20 % of the executed instructions.
+template <int KIND, bool EDGE>
+__device__ __forceinline__ void chunk_compute(const uint32_t (&r)[32], float2 scl2, float2 a2s, const float* al_row,
+                                              unsigned char* gout_row, int nfirst, int N, float2& v) {
+#pragma unroll
+  for (int k8 = 0; k8 < 4; ++k8) {             // 8 columns -> 16 bytes of hi and of lo in this lane's staging row
+    unsigned ph[4], pl[4];
+    const float4 a0 = *reinterpret_cast<const float4*>(al_row + 8 * k8);
+    const float4 a1 = *reinterpret_cast<const float4*>(al_row + 8 * k8 + 4);
+    const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = 8 * k8 + 2 * i;
+      float2 r2 = __fmul2_rn(make_float2(__uint_as_float(r[col]), __uint_as_float(r[col + 1])), scl2);
+      r2.x = fmaxf(r2.x, 0.f);                 // the (hi, lo) products can leave -1 ulp at coincident points
+      r2.y = fmaxf(r2.y, 0.f);
+      float2 kk = kernel_pair_fast_t<KIND>(r2);
+      if (EDGE) {                              // padded observations carry no covariance
+        const int n = nfirst + col;
+        if (n >= N) kk.x = 0.f;
+        if (n + 1 >= N) kk.y = 0.f;
+      }
+      v = __ffma2_rn(kk, ap[i], v);
+      const float2 val = __fmul2_rn(kk, a2s);
+      const __half2 h2 = __floats2half2_rn(val.x, val.y);
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(val.x - hf.x, val.y - hf.y);
+      ph[i] = h2_bits(h2);
+      pl[i] = h2_bits(l2);
+    }
+    *reinterpret_cast<uint4*>(gout_row + k8 * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(gout_row + 64 + k8 * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -211,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
 #pragma unroll
         for (int d = 0; d < MAXD; ++d) xn[d] = __ldg(p.Xp + (size_t)d * p.Np + nbn * TN + r);
         const int st = (int)(t % BSTAGES);
-        mbar_wait(&b_empty[st], (uint32_t)(((t / BSTAGES) & 1) ^ 1));
+        mbar_wait_relaxed(&b_empty[st], (uint32_t)(((t / BSTAGES) & 1) ^ 1));
         const bool stamp = p.tl && blockIdx.x == 0 && t < TL_TILES;
         if (stamp && tid == 0) p.tl[t * 8 + 0] = clock64();
         unsigned char* bh = sB + (size_t)st * 2 * BH;
@@ -294,6 +331,34 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
     const int gt = tid - 128 - grp * 128;             // thread index inside the group (0..127) == accumulator row L
     const int bar_id = 2 + grp;
     long t = 0;
+    // alpha_s[n .. n+31] of the chunk starting at observation n, for all samples: this thread's share (coalesced 128-byte
+    // row reads), kept in registers until the group's shared-memory copy may be overwritten.  The loads of chunk c+1 are
+    // issued before chunk c is computed, so their latency never sits between the two barriers of a chunk.
+    constexpr int APF = MAXS * (CW / 4) / 128;          // float4 per thread at the sample limit (4)
+    float4 apf[APF];
+    auto alpha_fetch = [&](int nbase) {
+#pragma unroll
+      for (int q = 0; q < APF; ++q) {
+        const int f = gt + q * 128;
+        if (f < p.S * (CW / 4)) {
+          const int rs = f >> 3, c4 = (f & 7) * 4, n = nbase + c4;
+          const float* src = p.alpha + (size_t)rs * p.Npad_alpha + n;
+          if (n + 3 < p.N) apf[q] = __ldg(reinterpret_cast<const float4*>(src));
+          else apf[q] = make_float4(n < p.N ? src[0] : 0.f, n + 1 < p.N ? src[1] : 0.f, n + 2 < p.N ? src[2] : 0.f, 0.f);
+        }
+      }
+    };
+    auto alpha_store = [&]() {
+#pragma unroll
+      for (int q = 0; q < APF; ++q) {
+        const int f = gt + q * 128;
+        if (f < p.S * (CW / 4)) *reinterpret_cast<float4*>(gal + (size_t)(f >> 3) * ALD + (f & 7) * 4) = apf[q];
+      }
+    };
+    {                                                    // first chunk of this group: tile nb = grp of the first item
+      const int nb_first = grp % nblocks;
+      alpha_fetch(nb_first * TN);
+    }
     for (long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int crow = (int)item * p.J + j;           // candidate row inside the chunk
       const bool act = row_used && crow < p.mc_used;
@@ -307,7 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         const bool edge = n0 + TN > p.N;
         const bool stamp = p.tl && blockIdx.x == 0 && t < TL_TILES && q4 == 0 && lane == 0;
         if (stamp) p.tl[t * 8 + 5] = clock64();
-        mbar_wait(&t_full[b], (uint32_t)((t / TBUF) & 1));
+        mbar_wait_relaxed(&t_full[b], (uint32_t)((t / TBUF) & 1));
         if (stamp) p.tl[t * 8 + 6] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)b * TN;
@@ -315,47 +380,15 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         for (int cq = 0; cq < TN; cq += CW) {
           uint32_t r[32];
           tmem_ld32(t0 + cq, r);
-          // alpha_s[n0+cq .. +31] for all samples -> shared memory with coalesced 128-byte row reads
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // previous chunk's readers are done
-          for (int f = gt; f < p.S * (CW / 4); f += 128) {
-            const int rs = f >> 3, c4 = (f & 7) * 4, n = n0 + cq + c4;
-            const float* src = p.alpha + (size_t)rs * p.Npad_alpha + n;
-            float4 a4;
-            if (n + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(src));
-            else a4 = make_float4(n < p.N ? src[0] : 0.f, n + 1 < p.N ? src[1] : 0.f, n + 2 < p.N ? src[2] : 0.f, 0.f);
-            *reinterpret_cast<float4*>(gal + (size_t)rs * ALD + c4) = a4;
-          }
+          alpha_store();                                                         // this chunk's alpha: fetched a chunk ago
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // (also publishes rowoff of a new item)
+          // next chunk of this group: same tile, or the group's next tile (t + NGRP; alpha does not depend on the item)
+          alpha_fetch((cq + CW < TN) ? n0 + cq + CW : (int)(((t + NGRP) % nblocks) * TN));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (act) {
-#pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {             // 8 columns -> 16 bytes of hi and of lo in this lane's staging row
-              unsigned ph[4], pl[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int col = 8 * k8 + 2 * i;
-                float2 r2 = __fmul2_rn(make_float2(__uint_as_float(r[col]), __uint_as_float(r[col + 1])), scl2);
-                r2.x = fmaxf(r2.x, 0.f);                 // the (hi, lo) products can leave -1 ulp at coincident points
-                r2.y = fmaxf(r2.y, 0.f);
-                float2 kk = kernel_pair_fast(p.kind, r2);
-                if (edge) {                              // padded observations carry no covariance
-                  const int n = n0 + cq + col;
-                  if (n >= p.N) kk.x = 0.f;
-                  if (n + 1 >= p.N) kk.y = 0.f;
-                }
-                const float4 a4 = *reinterpret_cast<const float4*>(al_row + (col & ~3));
-                const float2 ap = (col & 2) ? make_float2(a4.z, a4.w) : make_float2(a4.x, a4.y);
-                v = __ffma2_rn(kk, ap, v);
-                const float2 val = __fmul2_rn(kk, a2s);
-                const __half2 h2 = __floats2half2_rn(val.x, val.y);
-                const float2 hf = __half22float2(h2);
-                const __half2 l2 = __floats2half2_rn(val.x - hf.x, val.y - hf.y);
-                ph[i] = h2_bits(h2);
-                pl[i] = h2_bits(l2);
-              }
-              *reinterpret_cast<uint4*>(gout + lane * OLD + k8 * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              *reinterpret_cast<uint4*>(gout + lane * OLD + 64 + k8 * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            }
+            if (edge) chunk_compute<KIND, true>(r, scl2, a2s, al_row, gout + lane * OLD, n0 + cq, p.N, v);
+            else chunk_compute<KIND, false>(r, scl2, a2s, al_row, gout + lane * OLD, n0 + cq, p.N, v);
           }
           __syncwarp();
           // coalesced write-out: each store instruction covers 4 rows x (64 B hi, 64 B lo); lane -> (row, half, 16-byte piece)
@@ -419,6 +452,12 @@ bool kxt_tc_supported(int D, int S) {
   const int Dp = ktc::MAXD;
   return ktc::smem_bytes(ktc::slots(S, Dp) * Dp, S) <= (size_t)227 * 1024;
 }
+// Worth it?  An accumulator row is one (candidate slot, sample) pair and at most 3 slots fit the operand stage, so with few
+// samples most of the 128 TMEM lanes (= epilogue threads) idle: S = 5 uses 15 lanes and the SIMT generator is 3x faster there
+// (22 vs 6.6 ms per step of the 8-GPU per-rank shape); from half the lanes on the tensor-core generator wins.
+bool kxt_tc_preferred(int D, int S) {
+  return kxt_tc_supported(D, S) && ktc::slots(S, ktc::MAXD) * S >= 64;
+}
 
 int kxt_tc_ngroups(int) { return ktc::NGRP; }       // mean partial planes per chunk
 
@@ -481,10 +520,16 @@ int kxt_tc(void* ws, int kind, int N, int Np, int M, int c_begin, int Mc, int mc
   const int grid = (int)std::min<long>(a.nitems, num_sms());
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(ktc::kxt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  ktc::kxt_tc_kernel<<<grid, ktc::THREADS, smem, st>>>(a);
+  switch (kind) {
+    case 0: case 1: ktc::kxt_tc_kernel<1><<<grid, ktc::THREADS, smem, st>>>(a); break;
+    case 2: ktc::kxt_tc_kernel<2><<<grid, ktc::THREADS, smem, st>>>(a); break;
+    default: ktc::kxt_tc_kernel<3><<<grid, ktc::THREADS, smem, st>>>(a); break;
+  }
   count_launch();
   return check_launch("kxt_tc");
 }

@@ -258,12 +258,14 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
                                                      const float* __restrict__ mean, const float* __restrict__ alpha,
                                                      int Npad_alpha, __half* __restrict__ khi,
                                                      __half* __restrict__ klo, float* __restrict__ mu, int ldm) {
-  constexpr int T = 128, LDC = T + 2, LDX = T + kPad;
-  __shared__ __align__(16) float2 cs[kKD][LDC];   // scaled candidates, each value duplicated (v, v): packed-op operand
-  __shared__ __align__(16) float xs[kKD][LDX];    // MINUS the scaled observations [d][n]
-  float (*red)[T] = reinterpret_cast<float (*)[T]>(&cs[0][0]);   // [16][T] epilogue scratch (aliases the staging)
-  static_assert(16 * T * sizeof(float) <= sizeof(float2) * kKD * LDC, "reduction scratch must fit in the staging buffer");
-  static_assert((LDC * sizeof(float2)) % 16 == 0 && (LDX * sizeof(float)) % 16 == 0, "128-bit shared loads");
+  constexpr int T = 128, LDC = T + kPad, LDX = T + kPad;
+  // scaled candidates [d][c] and MINUS the scaled observations [d][n].  The kernel is shared-memory-bandwidth bound (per
+  // dimension and warp: LDS.128 wavefronts vs 64 packed math instructions), so the candidate values are stored once and
+  // duplicated into the (v, v) operand of the packed instructions in registers -- 4 instead of 6 LDS.128 per dimension.
+  __shared__ __align__(16) float cs[kKD][LDC];
+  __shared__ __align__(16) float xs[kKD][LDX];
+  __shared__ __align__(16) float red[16][T];      // epilogue scratch of the fused mean
+  static_assert((LDC * sizeof(float)) % 16 == 0 && (LDX * sizeof(float)) % 16 == 0, "128-bit shared loads");
   const int s = blockIdx.y, c0 = blockIdx.x * T;  // c0 relative to the chunk
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const float* ils = inv_ls + (long)s * D;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
         int row = e / kKD, dd = e % kKD, d = d0 + dd;
         int gc = min(c_begin + c0 + row, M - 1), n = n0 + row;
         float sc = (d < D) ? ils[d] : 0.f;
-        cs[dd][row] = dup2((d < D) ? Cc[(long)gc * D + d] * sc : 0.f);
+        cs[dd][row] = (d < D) ? Cc[(long)gc * D + d] * sc : 0.f;
         xs[dd][row] = (d < D && n < N) ? -X[(long)n * D + d] * sc : 0.f;
       }
       __syncthreads();
@@ -302,9 +304,7 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const float4 p0 = *reinterpret_cast<const float4*>(&cs[dd][g * 64 + ty * 4]);
-          const float4 p1 = *reinterpret_cast<const float4*>(&cs[dd][g * 64 + ty * 4 + 2]);
-          const float2 a[4] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y),
-                               make_float2(p1.z, p1.w)};
+          const float2 a[4] = {dup2(p0.x), dup2(p0.y), dup2(p0.z), dup2(p0.w)};
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
@@ -524,7 +524,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           const Item it = get_item(p, w, h);
           if (!it.valid) break;
           for (int kc = 0; kc < it.nk; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_wait_relaxed(&empty[stage], phase ^ 1);     // the TMA thread sleeps until a stage is free
             unsigned char* sb = base + stage * STAGE_BYTES;
             const int kk = it.k0 + kc * bk;
             mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -593,7 +593,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         if (!it.valid) break;
         // undo the exact power-of-two operand scaling of the fp16 path
         const float scl = p.f16 ? ldexpf(1.f, -(kx_exp(p.amp2[it.s]) + p.bexp[it.s])) : 1.f;
-        mbar_wait(&tfull[buf], bphase);
+        mbar_wait_relaxed(&tfull[buf], bphase);              // epilogue warps sleep through the item's MMAs (tens of us)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
 #pragma unroll 1
@@ -748,6 +748,7 @@ static int make_map_h(CUtensorMap* m, const __half* ptr, uint64_t rows, uint64_t
 int num_sms();
 // tensor-core cross-covariance generator (kxt_tc.cu)
 bool kxt_tc_supported(int D, int S);
+bool kxt_tc_preferred(int D, int S);
 int kxt_tc_ngroups(int Np);
 size_t kxt_tc_workspace_bytes(int Np, int Mc, int S, int M, int D);
 int kxt_tc_prepare(void* ws, int N, int Np, int M, int Mc, int D, int S, const float* X, const float* Cc, cudaStream_t st);
@@ -1051,11 +1052,12 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   __half* ahi = reinterpret_cast<__half*>(partial + (size_t)npairs * S * Mc);   // alpha^T hi | lo  [S][Fp][Np]
   __half* alo = ahi + (size_t)S * Fp * Np;
   int* fexp = reinterpret_cast<int*>(alo + (size_t)S * Fp * Np);
-  // generator: the packed-float32 SIMT kernel is the production path (62-65 ms at the headline); the tensor-core
-  // generator of kxt_tc.cu (56-59 ms, parity-complete) is opt-in until verified as the default: SMK_KXT_IMPL=tc
+  // generator: the tensor-core kernel of kxt_tc.cu (contraction over dimensions on tcgen05) wherever it applies (D <= 32,
+  // shared-memory budget permitting; 59 vs 73 ms per headline step on the same box, round 2) -- the packed-float32 SIMT
+  // kernel otherwise, or when asked for with SMK_KXT_IMPL=simt
   static int gen_env = -1;
-  if (gen_env < 0) { const char* e = getenv("SMK_KXT_IMPL"); gen_env = (e && !strcmp(e, "tc")) ? 1 : 0; }
-  const bool gen_tc = gen_env == 1 && kxt_tc_supported(D, S) && nbuf == 1;
+  if (gen_env < 0) { const char* e = getenv("SMK_KXT_IMPL"); gen_env = (e && !strcmp(e, "simt")) ? 0 : 1; }
+  const bool gen_tc = gen_env == 1 && kxt_tc_preferred(D, S) && nbuf == 1;
   const int nmp = gen_tc ? kxt_tc_ngroups(Np) : 0;
   void* kws = reinterpret_cast<void*>(fexp + S);
   float* mu_partial = gen_tc ? kxt_tc_mu_partial(kws, Np, Mc, S, M, D) : nullptr;

@@ -49,6 +49,21 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float2 dup2(float x) { return make_float2(x, x); }
+template <int KIND>
+__device__ __forceinline__ float2 kernel_pair_fast_t(float2 r2) {      // same arithmetic, kind resolved at compile time
+  constexpr float kL2E = 1.4426950408889634f;
+  if (KIND <= 1) {
+    const float2 t = __fmul2_rn(r2, dup2(-0.5f * kL2E));
+    return make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  }
+  const float2 r = make_float2(sqrt_approx(r2.x), sqrt_approx(r2.y));
+  constexpr float c = (KIND == 2) ? 1.7320508075688772f : 2.23606797749979f;
+  const float2 t = __fmul2_rn(r, dup2(-c * kL2E));
+  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  float2 p = __ffma2_rn(r, dup2(c), dup2(1.f));
+  if (KIND == 3) p = __ffma2_rn(r2, dup2(5.0f / 3.0f), p);
+  return __fmul2_rn(p, e);
+}
 __device__ __forceinline__ float2 kernel_pair_fast(int kind, float2 r2) {
   constexpr float kL2E = 1.4426950408889634f;
   if (kind <= 1) {                                            // SE / ARDSE: exp(-r2 / 2)
@@ -80,6 +95,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" ::"r"(smem_u32(bar)),
       "r"(parity)
+      : "memory");
+}
+// Same wait for threads that expect to wait LONG (a producer on a free stage, an epilogue warp on its next accumulator): the
+// try_wait carries a suspend-time hint, so the thread sleeps in hardware instead of spinning through the issue slots (and the
+// power budget) of the warps that are doing the work.  ncu of the generator: SYNCS + YIELD + BRA of the spin loops were ~20 %
+// of all executed instructions.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP_R:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE_R;\n\t"
+      "bra WAIT_LOOP_R;\n\t"
+      "DONE_R:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20000u)
       : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {

@@ -54,6 +54,16 @@ class HyperBatch(object):
         self.host_mean, self.host_noise, self.host_amp2, self.host_ls = mean, noise, amp2, ls
         self.nbytes = host.size * (8 if dtype == torch.float64 else 4)
 
+    def slice(self, a, b):
+        """Samples a..b-1 as a HyperBatch of their own (views of the same device memory)."""
+        o = object.__new__(HyperBatch)
+        o.S, o.D = b - a, self.D
+        o.mean, o.noise, o.amp2, o.inv_ls = self.mean[a:b], self.noise[a:b], self.amp2[a:b], self.inv_ls[a:b]
+        o.host_mean, o.host_noise = self.host_mean[a:b], self.host_noise[a:b]
+        o.host_amp2, o.host_ls = self.host_amp2[a:b], self.host_ls[a:b]
+        o.nbytes = 0
+        return o
+
 
 class Factor(object):
     """Batched Cholesky factors of K_s = amp2_s (k + 1e-6 I) + noise_s I for S hyper-samples."""
@@ -234,25 +244,35 @@ class GPEIEngine(object):
         self.last = {}
         self.last_guard = None
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
-        self._pool = {}      # (shape, dtype) -> free tensors: the big per-call buffers are recycled, never re-allocated
+        self._pool = {}      # (stream, shape, dtype) -> free tensors: the big per-call buffers are recycled, never re-allocated
+        self._home = {}      # data_ptr -> stream the buffer belongs to
+        self._side = None    # second stream: the factor chain of one half of the samples runs under the other half's GEMM
+        # measured: no gain (268.8 -> 272.6 ms at S=40, 37.8 -> 39.9 ms at S=5): the persistent GEMM and the generator leave no
+        # SM for the side stream's kernels to run on, and two groups double the launches.  Off unless asked for.
+        self.overlap = os.environ.get("SMK_FACTOR_OVERLAP", "0") == "1"
         self._helper64 = None
 
     # ------------------------------------------------------------------ buffers
     def take(self, shape, dtype=None):
         """A device buffer of exactly this shape from the engine's free list (allocated on first use only).  The C library
         never allocates; this is the host-side mirror of that rule: steady-state calls reuse the same HBM."""
-        key = (tuple(int(x) for x in shape), dtype or self.dtype)
+        # one free list per stream: a buffer given back right after its last launch may be taken again at once, which is
+        # only ordered correctly among launches of the SAME stream
+        key = (torch.cuda.current_stream(self.device).cuda_stream, tuple(int(x) for x in shape), dtype or self.dtype)
         free = self._pool.get(key)
         if free:
             return free.pop()
         try:
-            return torch.empty(key[0], dtype=key[1], device=self.device)
+            t = torch.empty(key[1], dtype=key[2], device=self.device)
         except torch.cuda.OutOfMemoryError:
             self.trim()                       # buffers of other shapes are the only thing the pool can be blamed for
-            return torch.empty(key[0], dtype=key[1], device=self.device)
+            t = torch.empty(key[1], dtype=key[2], device=self.device)
+        self._home[t.data_ptr()] = key[0]
+        return t
 
     def trim(self):
         self._pool.clear()
+        self._home.clear()
         torch.cuda.empty_cache()
 
     def pooled_bytes(self):
@@ -260,8 +280,9 @@ class GPEIEngine(object):
 
     def give(self, *tensors):
         for t in tensors:
-            if t is not None:
-                self._pool.setdefault((tuple(t.shape), t.dtype), []).append(t)
+            if t is not None:          # back to the free list of the stream it was taken on
+                home = self._home.get(t.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+                self._pool.setdefault((home, tuple(t.shape), t.dtype), []).append(t)
 
     def helper64(self):
         """The float64 engine on the same device (pending-point conditionals, deep-tail re-evaluation)."""
@@ -641,6 +662,10 @@ class GPEIEngine(object):
         chunk = self.max_samples_per_chunk(_ceil(N + P, 128), ldm, Fn)
         ei_sum = torch.zeros((ldm,), dtype=torch.float64, device=self.device)
         ei_all = torch.empty((S, ldm), dtype=torch.float64, device=self.device) if want_matrix else None
+        if chunk >= S and self.can_overlap(N, S, P, time_hyper_samples):
+            self._two_group_pass(kind, hyper_samples, comp, cand, vals, res, Cd, want_matrix, ei_sum, ei_all)
+            self.last = dict(N=N, M=M, S=S, P=P, chunk=chunk, groups=2)
+            return ei_all, ei_sum, M
         for s0 in range(0, S, chunk):
             r = res if (res is not None and chunk >= S) else (dict(res, hb=None) if res is not None else None)
             nrm = normals[s0:s0 + chunk] if (normals is not None and np.ndim(normals) == 3) else normals
@@ -654,6 +679,57 @@ class GPEIEngine(object):
             del prep
         self.last = dict(N=N, M=M, S=S, P=P, chunk=chunk)
         return ei_all, ei_sum, M
+
+    def can_overlap(self, N, S, P, time_hyper_samples):
+        return (self.overlap and S >= 4 and P == 0 and time_hyper_samples is None and self.chain_for(N) == "tc")
+
+    def prepare_two_groups(self, kind, hyper_samples, comp, vals, res=None):
+        """[prep of the first half, prep of the second half]: the factor chain (K build, Cholesky, inverse, operand pack:
+        ~18 % of the headline step, latency-bound, a handful of SMs busy) of the SECOND half is queued on a side stream, so
+        that it runs underneath the cross-covariance generator and predict GEMM of the FIRST half (ei_groups).  The chain is
+        low-power work, so unlike overlapping the generator with the GEMM (both at the power cap: slower, DESIGN.md section
+        5) this does not cost the GEMM its clock.  On 8 GPUs (5 samples per rank) it hides most of the latency floor that
+        round 1's scaling run ran into."""
+        S = len(hyper_samples)
+        h = (S + 1) // 2
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+        if res is not None:                       # inputs already resident: group views of the caller's tensors
+            hb = res.get("hb")
+            r0 = dict(res, hb=hb.slice(0, h) if hb is not None else None)
+            r1 = dict(res, hb=hb.slice(h, S) if hb is not None else None)
+        else:                                     # upload once, share between the groups
+            shared = dict(X=self.to_dev(comp), y=self.to_dev(vals), best=float(np.min(vals)))
+            r0, r1 = dict(shared, hb=None), dict(shared, hb=None)
+        prep0 = self.prepare(kind, hyper_samples[:h], comp, None, vals, None, None, None, resident=r0)
+        side.wait_stream(main)                    # inputs uploaded; everything of the previous call is behind us
+        with torch.cuda.stream(side):
+            prep1 = self.prepare(kind, hyper_samples[h:], comp, None, vals, None, None, None, resident=r1)
+            prep1.ready = side.record_event()
+        prep0.ready = None
+        return [prep0, prep1]
+
+    def ei_groups(self, preps, Cd, want_matrix, ei_sum, cand_host=None):
+        """EI of every candidate for the samples of all groups, in order; waits for a group's factor chain only when its turn
+        comes.  Returns (ei [S][ldm] | None, ei_sum)."""
+        main = torch.cuda.current_stream(self.device)
+        parts = []
+        for p in preps:
+            if getattr(p, "ready", None) is not None:
+                main.wait_event(p.ready)
+            ei, ei_sum = self.ei_prepared(p, Cd, want_matrix, ei_sum, cand_host=cand_host)
+            parts.append(ei)
+        return (torch.cat(parts, dim=0) if want_matrix else None), ei_sum
+
+    def _two_group_pass(self, kind, hyper_samples, comp, cand, vals, res, Cd, want_matrix, ei_sum, ei_all):
+        preps = self.prepare_two_groups(kind, hyper_samples, comp, vals, res)
+        ei, _ = self.ei_groups(preps, Cd, want_matrix, ei_sum, cand_host=cand)
+        for p in preps:
+            p.fac.check_pd()                      # host syncs after everything is queued
+        if want_matrix:
+            ei_all[:] = ei
 
     def ei_over_hypers(self, kind, hyper_samples, comp, pend, cand, vals, normals=None,
                        time_hyper_samples=None, durs_log=None):
