@@ -33,10 +33,6 @@ __device__ long long g_diag_tl[64];
 #define DIAG_STAMP(i) do { } while (0)
 #endif
 
-template <typename T> __device__ __forceinline__ T smk_rsqrt(T x);
-template <> __device__ __forceinline__ float smk_rsqrt<float>(float x) { return 1.0f / sqrtf(x); }
-template <> __device__ __forceinline__ double smk_rsqrt<double>(double x) { return rsqrt(x); }
-
 template <typename T> struct TileLd { static constexpr int v = 33; };
 template <> struct TileLd<double> { static constexpr int v = 36; };
 
@@ -44,8 +40,8 @@ template <typename T, int NB>
 struct DiagSmem {
   static constexpr int SB = 32, LDT = TileLd<T>::v, NP = NB / SB, NT = NP * (NP + 1) / 2;
   static constexpr int TILE = SB * LDT;
-  // a tiles (lower block triangle) | NP diagonal inverse tiles | broadcast column [32] | inverse pivots [NB]
-  static constexpr size_t bytes = sizeof(T) * ((size_t)(NT + NP) * TILE + 32 + NB);
+  // a tiles (lower block triangle) | NP diagonal inverse tiles | broadcast columns [2][32] (16-byte aligned) | inverse pivots [NB]
+  static constexpr size_t bytes = sizeof(T) * ((size_t)(NT + NP) * TILE + 64 + NB);
   static __host__ __device__ __forceinline__ int tile(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * TILE; }
 };
 
@@ -102,68 +98,138 @@ __device__ __forceinline__ void blk_coord(const BlkAcc<float>&, int i, int j, in
 }
 
 // ------------------------------------------------------------------------------------------------ 32 x 32 pieces
-// Lower Cholesky of the 32 x 32 piece at `a` (tile, row stride LDT) by the calling warp; lane = row.
-// `col` is a 32-entry broadcast buffer, ipv receives 1 / L_jj.  `bad`: first non-positive pivot (or -1).
+// 1 / sqrt(x) without a branch: hardware seed (MUFU, ~2^-22) and one third-order step  y = y0 + y0 e (1/2 + 3/8 e),
+// e = 1 - x y0^2  (remainder 5/16 e^3 ~ 2^-65; ~1 ulp).  The library rsqrt(double) / 1.0f / sqrtf() carry a slow-path branch
+// and 7-8 DEPENDENT operations; on the pivot chain of a Cholesky step that latency is paid once per column.
+template <typename T> __device__ __forceinline__ T fast_rsqrt(T x);
+template <> __device__ __forceinline__ double fast_rsqrt<double>(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double t = x * y0, e = fma(-t, y0, 1.0);
+  return fma(y0 * e, fma(0.375, e, 0.5), y0);
+}
+template <> __device__ __forceinline__ float fast_rsqrt<float>(float x) {
+  const float y0 = rsqrtf(x);
+  const float t = x * y0, e = fmaf(-t, y0, 1.f);
+  return fmaf(y0 * e, fmaf(0.375f, e, 0.5f), y0);
+}
+template <typename T> struct Vec16;
+template <> struct Vec16<double> { typedef double2 type; static constexpr int n = 2; };
+template <> struct Vec16<float> { typedef float4 type; static constexpr int n = 4; };
+__device__ __forceinline__ double vget(const double2& v, int i) { return i ? v.y : v.x; }
+__device__ __forceinline__ float vget(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// Lower Cholesky of the 32 x 32 piece at `a` (tile, row stride LDT) by the calling warp; lane = row, the row lives in
+// registers.  `col`: 64-entry, 16-byte aligned broadcast buffer; ipv receives 1 / L_jj; st ([32][32], 16-byte aligned)
+// receives the scaled transpose  st[m][k] = L[k][m] / L[k][k]  (k > m) that fwd_subst32 reads.  `bad`: first non-positive
+// pivot (or -1).
+//
+// What bounds it is the chain  pivot -> rsqrt -> scale -> (column to the other lanes) -> update -> next pivot, once per
+// column, and -- the whole piece being straight-line code that runs once -- the instruction stream itself
+// (tools/microbench/chol32_bench.cu, profiles/r02_diag_timeline.md):
+//   * the next pivot  r[j+1] - l^2  needs no other lane's data: lane j+1 forms it from its own l, so the broadcast of the
+//     column is off the chain (183 cycles per column in float64 against 267, 140 against 252 in float32);
+//   * the column is broadcast through shared memory with 16-byte loads instead of one shuffle per element: 3.5 k
+//     instructions per piece instead of 9.7 k (float64), and the function is NOT inlined -- one copy for all call sites,
+//     because the first execution of every further copy cost ~10 k cycles of instruction fetch.
 template <typename T>
-__device__ __forceinline__ void warp_chol32(T* a, T* col, T* ipv, int lane, int& bad) {
-  constexpr int LDT = TileLd<T>::v;
-  (void)col;
+__device__ __noinline__ void warp_chol32(T* a, T* col, T* ipv, T* st, int lane, int& bad) {
+  constexpr int LDT = TileLd<T>::v, NV = Vec16<T>::n;
+  typedef typename Vec16<T>::type V;
   T r[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) r[k] = (k <= lane) ? a[lane * LDT + k] : T(0);
-  // Column step j: pivot from lane j, every lane scales its entry, then row k of the update needs l of lane k -- all by
-  // register shuffles: no shared-memory round trip and no warp barrier inside the piece, so the compiler overlaps the
-  // update of step j with the pivot chain (shuffle -> rsqrt -> multiply -> shuffle -> fma) of step j + 1.
+  T piv = r[0];                                  // this lane's candidate for the pivot of the next column (valid at lane j)
+  T myip = T(0);
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    T d = __shfl_sync(0xffffffffu, r[j], j);
+    T d = __shfl_sync(0xffffffffu, piv, j);
     if (!(d > T(0))) { if (bad < 0) bad = j; d = T(1); }
-    const T ip = smk_rsqrt<T>(d);
+    const T ip = fast_rsqrt<T>(d);
     const T l = r[j] * ip;                       // lane j: d / sqrt(d) = sqrt(d)
     if (lane >= j) r[j] = l;
-    if (lane == j) ipv[j] = ip;
+    if (lane == j) { ipv[j] = ip; myip = ip; }
+    if (j < 31) piv = fma(-l, l, r[j + 1]);      // bitwise what the update below leaves in r[j+1] of lane j+1
+    T* cb = col + (j & 1) * 32;                  // two buffers: one warp barrier per column
+    cb[lane] = l;
+    __syncwarp();
+    const V* cv = reinterpret_cast<const V*>(cb);
 #pragma unroll
-    for (int k = j + 1; k < 32; ++k) {
-      const T lk = __shfl_sync(0xffffffffu, l, k);
-      r[k] = fma(-l, lk, r[k]);                  // meaningful for j < k <= lane
+    for (int q = (j + 1) / NV; q < 32 / NV; ++q) {
+      const V v = cv[q];                         // same address in every lane: broadcast
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int k = q * NV + i;
+        if (k > j) r[k] = fma(-l, vget(v, i), r[k]);      // meaningful for j < k <= lane
+      }
     }
   }
 #pragma unroll
-  for (int k = 0; k < 32; ++k)
+  for (int k = 0; k < 32; ++k) {
     if (k <= lane) a[lane * LDT + k] = r[k];
+    st[k * 32 + lane] = r[k] * myip;             // row k of st = column k of L, every row scaled by its inverse pivot
+  }
 }
 
-// W = L^-1 of a 32 x 32 lower-triangular tile by the calling warp; lane = column c, the column lives in registers.
+// Forward substitution  L y = b  for one right-hand side per thread, in place (x: b in, y out); L as the scaled transpose
+// st written by warp_chol32, ipv = 1 / L_kk.  Right-looking with pre-scaled multipliers:
+//     x_k <- b_k / L_kk;   for m = 0..31:  x_k -= (L_km / L_kk) x_m  for all k > m
+// so the step from x_m to x_m+1 is ONE fused multiply-add (the left-looking form  x_k = (b_k - sum_m L_km x_m) / L_kk  puts
+// a multiply-add, the reduction of its partial sums and the scaling on that chain: 2.5 - 3.7 k cycles per 32 x 32 piece in
+// the timeline against ~1 k), and every read is a 16-byte broadcast load of a row of st.
 template <typename T>
-__device__ __forceinline__ void warp_trinv32(const T* l, const T* ipv, T* w, int lane) {
+__device__ __forceinline__ void fwd_subst32(const T* st, const T* ipv, T (&x)[32]) {
+  constexpr int NV = Vec16<T>::n;
+  typedef typename Vec16<T>::type V;
+#pragma unroll
+  for (int q = 0; q < 32 / NV; ++q) {
+    const V v = reinterpret_cast<const V*>(ipv)[q];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) x[q * NV + i] *= vget(v, i);
+  }
+#pragma unroll
+  for (int m = 0; m < 31; ++m) {
+    const V* row = reinterpret_cast<const V*>(st + m * 32);
+#pragma unroll
+    for (int q = (m + 1) / NV; q < 32 / NV; ++q) {
+      const V v = row[q];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int k = q * NV + i;
+        if (k > m) x[k] = fma(-vget(v, i), x[m], x[k]);
+      }
+    }
+  }
+}
+
+// W = L^-1 of a 32 x 32 lower-triangular tile by the calling warp: lane = column c solves L w = e_c.  st / ipv as above;
+// w (tile, row stride LDT) may be the memory st lives in (every lane has read all it needs before the first write).
+template <typename T>
+__device__ __forceinline__ void warp_trinv32(const T* st, const T* ipv, T* w, int lane) {
   constexpr int LDT = TileLd<T>::v;
   T x[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    T t0 = (i == lane) ? T(1) : T(0), t1 = T(0), t2 = T(0), t3 = T(0);
-#pragma unroll
-    for (int k = 0; k < i; ++k) {                // x[k] == 0 for k < lane: no lane-dependent bounds
-      const T lv = l[i * LDT + k];
-      if ((k & 3) == 0) t0 = fma(-lv, x[k], t0);
-      else if ((k & 3) == 1) t1 = fma(-lv, x[k], t1);
-      else if ((k & 3) == 2) t2 = fma(-lv, x[k], t2);
-      else t3 = fma(-lv, x[k], t3);
-    }
-    x[i] = (i >= lane) ? ((t0 + t1) + (t2 + t3)) * ipv[i] : T(0);
-  }
+  for (int i = 0; i < 32; ++i) x[i] = (i == lane) ? T(1) : T(0);
+  fwd_subst32<T>(st, ipv, x);                    // x[i] stays exactly 0 for i < lane
+  __syncwarp();
 #pragma unroll
   for (int i = 0; i < 32; ++i) w[i * LDT + lane] = x[i];
 }
 
 // rank-32 update of the lower triangle left of piece p:  C[r][c] -= X[r] . X[c]  for r >= c (rows relative to the first
-// remaining row; X = tiles (bi, p), C = tiles (bi, bj)).
+// remaining row; X = tiles (bi, p), C = tiles (bi, bj)).  Two parts, so that the NEXT diagonal piece can be factored while
+// the bulk of the update is still running (look-ahead inside the block):
+//   part 0: the tile (p+1, p+1) only, all 8 warps;   part 1: everything else, warps 1..7 (warp 0 is factoring).
 template <int NB>
-__device__ __forceinline__ void diag_update(double* a, int p) {
+__device__ __forceinline__ void diag_update(double* a, int p, int part) {
   using DS = DiagSmem<double, NB>;
   constexpr int LDT = DS::LDT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
   const int nt8 = (NB - (p + 1) * 32) / 8;                // 8 x 8 tiles per side
-  for (int e = warp; e < nt8 * (nt8 + 1) / 2; e += 8) {   // lower tile triangle, one DMMA tile per warp and round
+  // lower tile triangle in row-major order: entries 0..9 are exactly the tile rows 0..3 = the 32 x 32 tile (p+1, p+1)
+  const int e0 = part ? 10 + warp - 1 : warp, e1 = part ? nt8 * (nt8 + 1) / 2 : 10, step = part ? 7 : 8;
+  if (part && warp == 0) return;
+  for (int e = e0; e < e1; e += step) {                   // one DMMA tile per warp and round
     int tr = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
     while (tr * (tr + 1) / 2 > e) --tr;
     while ((tr + 1) * (tr + 2) / 2 <= e) ++tr;
@@ -180,13 +246,31 @@ __device__ __forceinline__ void diag_update(double* a, int p) {
   }
 }
 template <int NB>
-__device__ __forceinline__ void diag_update(float* a, int p) {
-  // A thread owns the 4 x 4 elements (gr + i nt, gc + j nt): consecutive lanes read consecutive rows of X (conflict-free,
-  // stride 33) and share the other operand (broadcast).  i > j is always below the diagonal, i == j iff gr >= gc.
+__device__ __forceinline__ void diag_update(float* a, int p, int part) {
   using DS = DiagSmem<float, NB>;
   constexpr int LDT = DS::LDT, SB = 32;
+  if (part == 0) {
+    // tile (p+1, p+1): thread (ty, tx) owns rows 2ty, 2ty+1 x columns 2tx, 2tx+1 (tx <= ty: the lower half)
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    if (tx > ty) return;
+    const float* x = a + DS::tile(p + 1, p);
+    const float *a0 = x + (2 * ty) * LDT, *b0 = x + (2 * tx) * LDT;
+    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < SB; ++k) {
+      const float x0 = a0[k], x1 = a0[LDT + k], y0 = b0[k], y1 = b0[LDT + k];
+      c00 = fmaf(x0, y0, c00); c01 = fmaf(x0, y1, c01); c10 = fmaf(x1, y0, c10); c11 = fmaf(x1, y1, c11);
+    }
+    float* ct = a + DS::tile(p + 1, p + 1) + (2 * ty) * LDT + 2 * tx;
+    ct[0] -= c00; ct[1] -= c01; ct[LDT] -= c10; ct[LDT + 1] -= c11;      // (2ty, 2tx+1) with tx == ty is above the diagonal: never read
+    return;
+  }
+  // everything else, threads 32..255.  A thread owns the 4 x 4 elements (gr + i nt, gc + j nt): consecutive lanes read
+  // consecutive rows of X (conflict-free, stride 33) and share the other operand (broadcast).  i > j is always below the
+  // diagonal, i == j iff gr >= gc.
+  if (threadIdx.x < 32) return;
   const int rows = NB - (p + 1) * SB, nt = rows / 4;
-  for (int e = threadIdx.x; e < nt * nt; e += 256) {
+  for (int e = threadIdx.x - 32; e < nt * nt; e += 224) {
     const int gr = e / nt, gc = e % nt;
     const bool dg = gr >= gc;
     const float* xr[4];
@@ -218,6 +302,7 @@ __device__ __forceinline__ void diag_update(float* a, int p) {
       for (int j = 0; j <= i; ++j) {
         if (i == j && !dg) continue;
         const int r = gr + i * nt, c = gc + j * nt;
+        if (r < SB && c < SB) continue;                     // tile (p+1, p+1): part 0
         a[DS::tile(p + 1 + (r >> 5), p + 1 + (c >> 5)) + (r & 31) * LDT + (c & 31)] -= acc[i][j];
       }
   }
@@ -232,9 +317,9 @@ __device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ wd
   using DS = DiagSmem<T, NB>;
   constexpr int SB = 32, LDT = DS::LDT, NP = DS::NP, TILE = DS::TILE;
   T* a = sm;
-  T* w = a + DS::NT * TILE;                 // NP diagonal inverse tiles
+  T* w = a + DS::NT * TILE;                 // NP tiles: scaled transposes of the diagonal pieces, then their inverses
   T* col = w + NP * TILE;
-  T* ipv = col + 32;
+  T* ipv = col + 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   DIAG_STAMP(0);
@@ -256,64 +341,73 @@ __device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ wd
   __syncthreads();
   DIAG_STAMP(1);
 
-  for (int p = 0; p < NP; ++p) {
-    // (a) diagonal piece
-    if (warp == 0) {
-      int bad = -1;
-      warp_chol32<T>(a + DS::tile(p, p), col, ipv + p * SB, lane, bad);
-      if (bad >= 0 && lane == 0 && info && *info == 0) *info = info_base + p * SB + bad + 1;
-    }
-    __syncthreads();
-    DIAG_STAMP(2 + 4 * p);
+  // Look-ahead inside the block: after the substitution of piece p the tile (p+1, p+1) is updated first (all warps, a few
+  // hundred cycles); then warp 0 factors piece p+1 while warps 1..7 finish the rank-32 update and store the finished block
+  // column p.  The critical path is  chol32 -> substitution -> one tile update -> chol32 ...; the bulk of the updates and
+  // of the stores hides behind the factorisations.
+  auto chol_piece = [&](int p) {
+    int bad = -1;
+    warp_chol32<T>(a + DS::tile(p, p), col, ipv + p * SB, w + p * TILE, lane, bad);
+    if (bad >= 0 && lane == 0 && info && *info == 0) *info = info_base + p * SB + bad + 1;
+  };
+  auto store_column = [&](int p) {                          // tiles (p..NP-1, p) are final; threads 32..255
+    for (int bi = p; bi < NP; ++bi)
+      for (int e = tid - 32; e < SB * SB; e += 224) {
+        const int i = e >> 5, k = e & 31;
+        if (p < bi || k <= i) Ab[(long)(bi * SB + i) * ld + p * SB + k] = a[DS::tile(bi, p) + i * LDT + k];
+      }
+  };
+  if (warp == 0) chol_piece(0);
+  __syncthreads();
+  DIAG_STAMP(2);
+  for (int p = 0; p + 1 < NP; ++p) {
     const int rows = NB - (p + 1) * SB;
-    if (rows == 0) break;
-    // (b) rows below: X L_pp^T = A_sub by substitution, one thread per row (x_k needs x_0..x_{k-1}: registers)
+    // (b) rows below: X L_pp^T = A_sub by substitution, one thread per row
     if (tid < rows) {
       const int bi = p + 1 + (tid >> 5);
       T* ar = a + DS::tile(bi, p) + (tid & 31) * LDT;
-      const T* lp = a + DS::tile(p, p);
-      const T* ip = ipv + p * SB;
       T x[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) x[k] = ar[k];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        T t0 = x[k], t1 = T(0), t2 = T(0), t3 = T(0);
-#pragma unroll
-        for (int m = 0; m < k; ++m) {
-          const T lv = lp[k * LDT + m];          // same address in every lane: broadcast
-          if ((m & 3) == 0) t0 = fma(-lv, x[m], t0);
-          else if ((m & 3) == 1) t1 = fma(-lv, x[m], t1);
-          else if ((m & 3) == 2) t2 = fma(-lv, x[m], t2);
-          else t3 = fma(-lv, x[m], t3);
-        }
-        x[k] = ((t0 + t1) + (t2 + t3)) * ip[k];
-      }
+      fwd_subst32<T>(w + p * TILE, ipv + p * SB, x);
 #pragma unroll
       for (int k = 0; k < 32; ++k) ar[k] = x[k];
     }
     __syncthreads();
     DIAG_STAMP(3 + 4 * p);
-    // (c) rank-32 update of the remaining lower triangle
-    diag_update<NB>(a, p);
+    // (c) rank-32 update: the next diagonal tile first ...
+    diag_update<NB>(a, p, 0);
     __syncthreads();
     DIAG_STAMP(4 + 4 * p);
+    // ... then the next piece's factorisation (warp 0) next to the rest of the update and the stores of column p
+#ifndef SMK_DIAG_LA
+#define SMK_DIAG_LA 3
+#endif
+    if (!(SMK_DIAG_LA & 1)) { diag_update<NB>(a, p, 1); __syncthreads(); }
+    if (!(SMK_DIAG_LA & 2)) { if (warp) store_column(p); __syncthreads(); }
+    DIAG_STAMP(4 + 4 * p);
+    if (warp == 0) { chol_piece(p + 1); DIAG_STAMP(5 + 4 * p); }
+    else {
+      if (SMK_DIAG_LA & 1) diag_update<NB>(a, p, 1);
+      if (SMK_DIAG_LA & 2) store_column(p);
+    }
+    __syncthreads();
+    DIAG_STAMP(6 + 4 * p);
   }
   DIAG_STAMP(20);
 
   // ---- inverses of the diagonal pieces, one warp each
-  if (warp < NP) warp_trinv32<T>(a + DS::tile(warp, warp), ipv + warp * SB, w + warp * TILE, lane);
+  if (warp < NP) warp_trinv32<T>(w + warp * TILE, ipv + warp * SB, w + warp * TILE, lane);
   __syncthreads();
   DIAG_STAMP(21);
 
-  // ---- store L (lower triangle) tile by tile and the compact diagonal inverses
-  for (int bi = 0; bi < NP; ++bi)
-    for (int bj = 0; bj <= bi; ++bj)
+  // ---- store what is left of L (the last diagonal tile; the block columns before it went out during the look-ahead) and
+  // the compact diagonal inverses
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int e = tid + q * 256, i = e >> 5, k = e & 31;
-        if (bj < bi || k <= i) Ab[(long)(bi * SB + i) * ld + bj * SB + k] = a[DS::tile(bi, bj) + i * LDT + k];
-      }
+  for (int q = 0; q < 4; ++q) {
+    const int e = tid + q * 256, i = e >> 5, k = e & 31;
+    if (k <= i) Ab[(long)((NP - 1) * SB + i) * ld + (NP - 1) * SB + k] = a[DS::tile(NP - 1, NP - 1) + i * LDT + k];
+  }
   for (int e = tid; e < NP * SB * SB; e += 256) {
     const int pp = e >> 10, i = (e >> 5) & 31, k = e & 31;
     wd[e] = (k <= i) ? w[pp * TILE + i * LDT + k] : T(0);

@@ -155,7 +155,10 @@ __device__ __forceinline__ void chunk_compute(const uint32_t (&r)[32], float2 sc
 template <int KIND>
 __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by OFFSET, not by integer arithmetic on the pointer: a pointer rebuilt from a uintptr_t loses its address
+  // space, and every shared-memory access of the kernel became a generic LD.E / ST.E on the long scoreboard (ncu r02:
+  // 38 % of all stall samples were long-scoreboard waits on what should have been LDS / STS).
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int Dp = p.Dp, K = p.K, C = K >> 3, CD = Dp >> 3;   // 16-byte k blocks per operand row / per candidate slot (4)
   const uint32_t BH = (uint32_t)TN * K * 2;          // bytes of one B half (hi or lo)
   const uint32_t WH = (uint32_t)128 * K * 2;

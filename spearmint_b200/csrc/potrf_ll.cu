@@ -3,9 +3,10 @@
 //
 // Round 1 ran this on the generic SIMT factorisation (NB = 64, 4 x 4 register tiles): 8.3 ms per N = 4096 matrix,
 // 2.8 TFLOP/s.  This file is the dedicated path:
-//   * NB = 128 block columns in pairs, right-looking, look-ahead on two streams: while the rank-256 update of the
-//     trailing matrix (pair j) runs, the next pair's diagonal blocks and panels are already being factored, so the
-//     serial spine  diag -> panel -> column update  hides behind the N^3/3 flops;
+//   * NB = 128 block columns in pairs, right-looking, look-ahead on three streams: while the rank-256 update of the
+//     trailing matrix (pair j) runs in the background, the next pair's diagonal blocks and panels are already being
+//     factored, and of the look-ahead updates only the one 128 x 128 block the next diagonal kernel reads stays on
+//     the serial spine  diag -> panel -> block update -> diag ...;
 //   * diagonal blocks by the warp-synchronous single-SM kernel of diag.cuh, panels by its block substitution;
 //   * the trailing updates (A_IK -= L_Ij L_Kj^T) as one tiled GEMM kernel on the fp64 tensor
 //     path: mma.sync.m8n8k4.f64 (DMMA), operands staged by cp.async through a 3-stage shared-memory ring
@@ -15,6 +16,7 @@
 // Only L (lower triangle) is produced; W_jj (inverse diagonal blocks) is internal workspace.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <map>
 #include <tuple>
 
@@ -22,6 +24,7 @@
 #include "diag.cuh"
 
 namespace smk {
+int num_sms();
 namespace ll {
 
 constexpr int NB = 128;
@@ -69,116 +72,197 @@ struct GemmArgs {
   int row0, col0;                        // first output row / column (elements) of tile (0, 0)
   int brow0;                             // first row of B for column tile 0
   int sub, tri;
+  int persist, nt, batch;                // persist = 1: grid-stride loop over the batch x lower-triangle tiles (nt per side)
 };
 
-template <int BM>
+template <int BM, int ST>
 __global__ void __launch_bounds__(256) dgemm_nt_kernel(GemmArgs g) {
   constexpr int WM = BM / 32, WN = 8 / WM;          // warp grid
   constexpr int WTN = 128 / WN;                     // columns per warp: 64 / 32 / 16
   constexpr int NT = WTN / 8;                       // 8-column DMMA tiles per warp
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* As = reinterpret_cast<double*>(smem_raw);           // [STAGES][BM][LDS]
-  double* Bs = As + STAGES * BM * LDS;                         // [STAGES][128][LDS]
+  double* As = reinterpret_cast<double*>(smem_raw);           // [ST][BM][LDS]
+  double* Bs = As + ST * BM * LDS;                             // [ST][128][LDS]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp / WN, wn = warp % WN, gq = lane >> 2, t4 = lane & 3;
-  const int r0 = g.row0 + blockIdx.x * BM, c0 = g.col0 + blockIdx.y * 128;
-  if (g.tri && c0 > r0 + BM - 1) return;            // the whole tile lies above the diagonal
-  const double* A = g.A + (long)blockIdx.z * g.a_stride + (long)r0 * g.lda;
-  const double* B = g.B + (long)blockIdx.z * g.b_stride + (long)(g.brow0 + blockIdx.y * 128) * g.ldb;
-  double* C = g.C + (long)blockIdx.z * g.c_stride + (long)r0 * g.ldc + c0;
-
-  auto load_stage = [&](int st, int k0) {
-    // 16-byte chunks: row = chunk / 8, piece = chunk % 8 (2 doubles each)
-#pragma unroll
-    for (int q = 0; q < BM * 8 / 256; ++q) {
-      const int ch = tid + q * 256, row = ch >> 3, pc = ch & 7;
-      cp_async16(As + ((size_t)st * BM + row) * LDS + pc * 2, A + (long)row * g.lda + k0 + pc * 2);
+  const int ntri = g.nt * (g.nt + 1) / 2;
+  const long items = g.persist ? (long)g.batch * ntri : 1;
+  for (long item = g.persist ? blockIdx.x : 0; item < items; item += gridDim.x) {
+    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (g.persist) {                                  // item -> (matrix, tile row >= tile column)
+      bz = (int)(item / ntri);
+      const int e = (int)(item - (long)bz * ntri);
+      bx = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+      while (bx * (bx + 1) / 2 > e) --bx;
+      while ((bx + 1) * (bx + 2) / 2 <= e) ++bx;
+      by = e - bx * (bx + 1) / 2;
     }
+    const int r0 = g.row0 + bx * BM, c0 = g.col0 + by * 128;
+    if (g.tri && c0 > r0 + BM - 1) continue;          // the whole tile lies above the diagonal
+    const double* A = g.A + (long)bz * g.a_stride + (long)r0 * g.lda;
+    const double* B = g.B + (long)bz * g.b_stride + (long)(g.brow0 + by * 128) * g.ldb;
+    double* C = g.C + (long)bz * g.c_stride + (long)r0 * g.ldc + c0;
+
+    auto load_stage = [&](int st, int k0) {
+      // 16-byte chunks: row = chunk / 8, piece = chunk % 8 (2 doubles each)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ch = tid + q * 256, row = ch >> 3, pc = ch & 7;
-      cp_async16(Bs + ((size_t)st * 128 + row) * LDS + pc * 2, B + (long)row * g.ldb + k0 + pc * 2);
+      for (int q = 0; q < BM * 8 / 256; ++q) {
+        const int ch = tid + q * 256, row = ch >> 3, pc = ch & 7;
+        cp_async16(As + ((size_t)st * BM + row) * LDS + pc * 2, A + (long)row * g.lda + k0 + pc * 2);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ch = tid + q * 256, row = ch >> 3, pc = ch & 7;
+        cp_async16(Bs + ((size_t)st * 128 + row) * LDS + pc * 2, B + (long)row * g.ldb + k0 + pc * 2);
+      }
+    };
+
+    double acc[4][NT][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+    const int nk = g.K / KC;
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) {
+      if (s < nk) load_stage(s, s * KC);
+      cp_async_commit();
     }
-  };
+    for (int kt = 0; kt < nk; ++kt) {
+      cp_async_wait<ST - 2>();
+      __syncthreads();
+      if (kt + ST - 1 < nk) load_stage((kt + ST - 1) % ST, (kt + ST - 1) * KC);
+      cp_async_commit();
+      const double* as = As + ((size_t)(kt % ST) * BM + wm * 32 + gq) * LDS + t4;
+      const double* bs = Bs + ((size_t)(kt % ST) * 128 + wn * WTN + gq) * LDS + t4;
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 4) {
+        double af[4], bf[NT];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) af[mi] = as[mi * 8 * LDS + kk];
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) bf[ni] = bs[ni * 8 * LDS + kk];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NT; ++ni) dmma(acc[mi][ni], af[mi], bf[ni]);
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();          // panel mode writes over its own A tile: every warp is done reading (and the ring is free)
 
-  double acc[4][NT][2];
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < NT; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-
-  const int nk = g.K / KC;
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) load_stage(s, s * KC);
-    cp_async_commit();
+      for (int ni = 0; ni < NT; ++ni) {
+        double2* cp = reinterpret_cast<double2*>(C + (long)(wm * 32 + mi * 8 + gq) * g.ldc + wn * WTN + ni * 8 + t4 * 2);
+        double2 v;
+        if (g.sub) { v = *cp; v.x -= acc[mi][ni][0]; v.y -= acc[mi][ni][1]; }
+        else { v.x = acc[mi][ni][0]; v.y = acc[mi][ni][1]; }
+        *cp = v;
+      }
   }
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    if (kt + STAGES - 1 < nk) load_stage((kt + STAGES - 1) % STAGES, (kt + STAGES - 1) * KC);
-    cp_async_commit();
-    const double* as = As + ((size_t)(kt % STAGES) * BM + wm * 32 + gq) * LDS + t4;
-    const double* bs = Bs + ((size_t)(kt % STAGES) * 128 + wn * WTN + gq) * LDS + t4;
-#pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
-      double af[4], bf[NT];
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) af[mi] = as[mi * 8 * LDS + kk];
-#pragma unroll
-      for (int ni = 0; ni < NT; ++ni) bf[ni] = bs[ni * 8 * LDS + kk];
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) dmma(acc[mi][ni], af[mi], bf[ni]);
-    }
+}
+
+// The one update the NEXT diagonal kernel waits for: block (b, b) -= P P^T with P = rows of block b, columns [k0, k0 + K) of
+// the factor (K = 128 after one panel, 256 for the look-ahead of a pair).  On the 32-row GEMM above (4 CTAs, 256 - 512
+// dependent DMMAs per warp) this took 12 - 18 us of every spine step (ncu launch list r02).  Here: one CTA per 32 x 32 tile
+// of the lower triangle (10 CTAs per matrix), both operand strips loaded in one burst of cp.async (every load in flight at
+// once), then K / 4 DMMAs per 8 x 8 tile in two independent chains -- 64 - 128 DMMAs per warp.
+constexpr int DBU_MAXK = 256;
+__global__ void __launch_bounds__(256) diag_block_update_kernel(int ld, int b, int k0, int K, double* __restrict__ A, long a_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int LD = K + 4;                              // row stride: 8-byte fragment loads hit distinct banks
+  double* Ar = reinterpret_cast<double*>(smem_raw);  // [32][LD] rows of the tile's row strip
+  double* Br = Ar + 32 * LD;                         // [32][LD] rows of its column strip
+  int ti = 0, e = blockIdx.x;                        // tile (ti, tj), ti >= tj, row-major over the lower triangle
+  while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+  const int tj = e - ti * (ti + 1) / 2;
+  double* As = A + (long)blockIdx.y * a_stride;
+  const double* pa = As + ((long)b * NB + ti * 32) * ld + k0;
+  const double* pb = As + ((long)b * NB + tj * 32) * ld + k0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+  const int cpr = K / 2;                             // 16-byte chunks per row
+  for (int ch = tid; ch < 32 * cpr; ch += 256) {
+    const int row = ch / cpr, pc = ch - row * cpr;
+    cp_async16(Ar + row * LD + pc * 2, pa + (long)row * ld + pc * 2);
+    cp_async16(Br + row * LD + pc * 2, pb + (long)row * ld + pc * 2);
   }
+  cp_async_commit();
   cp_async_wait<0>();
-  __syncthreads();          // panel mode writes over its own A tile: every warp is done reading
-
+  __syncthreads();
+  double* Ct = As + ((long)b * NB + ti * 32) * ld + (long)b * NB + tj * 32;
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < NT; ++ni) {
-      double2* cp = reinterpret_cast<double2*>(C + (long)(wm * 32 + mi * 8 + gq) * g.ldc + wn * WTN + ni * 8 + t4 * 2);
-      double2 v;
-      if (g.sub) { v = *cp; v.x -= acc[mi][ni][0]; v.y -= acc[mi][ni][1]; }
-      else { v.x = acc[mi][ni][0]; v.y = acc[mi][ni][1]; }
-      *cp = v;
+  for (int u = 0; u < 2; ++u) {
+    const int t = 2 * warp + u, r0 = (t >> 2) * 8, c0 = (t & 3) * 8;
+    const double* ap = Ar + (r0 + gq) * LD + t4;
+    const double* bp = Br + (c0 + gq) * LD + t4;
+    double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 8
+    for (int k = 0; k < K; k += 8) {
+      dmma(c[0], ap[k], bp[k]);
+      dmma(c[1], ap[k + 4], bp[k + 4]);
     }
+    double2* cp = reinterpret_cast<double2*>(Ct + (long)(r0 + gq) * ld + c0 + t4 * 2);
+    double2 v = *cp;
+    v.x -= c[0][0] + c[1][0];
+    v.y -= c[0][1] + c[1][1];
+    *cp = v;
+  }
 }
 
 template <int BM>
 static void launch_gemm(const GemmArgs& g, int tiles_m, int tiles_n, int S, cudaStream_t st) {
-  const size_t smem = sizeof(double) * STAGES * (BM + 128) * LDS;
+  constexpr int ST = STAGES;
+  const size_t smem = sizeof(double) * ST * (BM + 128) * LDS;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(dgemm_nt_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dgemm_nt_kernel<BM, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  dgemm_nt_kernel<BM><<<dim3(tiles_m, tiles_n, S), 256, smem, st>>>(g);
+  dgemm_nt_kernel<BM, ST><<<dim3(tiles_m, tiles_n, S), 256, smem, st>>>(g);
+}
+
+// The background update: 128 x 128 tiles of the lower triangle (nt per side) of S matrices as a grid-stride loop over at
+// most `ctas` CTAs.  Two things make room for the spine next to it (ptxas: 166 registers -> one CTA per SM):
+//   * ctas < number of SMs: the diagonal kernel (186 registers x 256 threads) cannot share an SM with this kernel, and a
+//     tile of it runs ~45 us -- launched over all SMs it made every diagonal block wait for a tile to drain;
+//   * a 2-stage ring (82 KB): the panel kernel (138 KB) and the 32-row GEMMs (77 KB) fit beside it on the same SM.
+static void launch_gemm_background(GemmArgs g, int nt, int S, int ctas, cudaStream_t st) {
+  constexpr int ST = 2;
+  const size_t smem = sizeof(double) * ST * (128 + 128) * LDS;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dgemm_nt_kernel<128, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  g.persist = 1; g.nt = nt; g.batch = S;
+  const long items = (long)S * nt * (nt + 1) / 2;
+  dgemm_nt_kernel<128, ST><<<(unsigned)std::min<long>(items, ctas), 256, smem, st>>>(g);
 }
 
 struct Streams {
-  cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t panel[2] = {nullptr, nullptr}, rest[2] = {nullptr, nullptr}, join = nullptr;
+  cudaStream_t main = nullptr, near = nullptr, side = nullptr;
+  cudaEvent_t diagblk = nullptr, col = nullptr, la = nullptr, larest = nullptr, larest2 = nullptr, panel = nullptr, rest = nullptr,
+              join_near = nullptr, join_side = nullptr;
 };
 static Streams& streams() {
   static Streams s;
   if (!s.main) {
-    cudaStreamCreateWithFlags(&s.main, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking);
-    for (int i = 0; i < 2; ++i) {
-      cudaEventCreateWithFlags(&s.panel[i], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&s.rest[i], cudaEventDisableTiming);
-    }
-    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);              // hi = numerically lowest = most urgent
+    cudaStreamCreateWithPriority(&s.main, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithPriority(&s.near, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi);   // the diagonal kernel needs an EMPTY SM: it goes first
+    cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, lo);
+    for (cudaEvent_t* e : {&s.diagblk, &s.col, &s.la, &s.larest, &s.larest2, &s.panel, &s.rest, &s.join_near, &s.join_side})
+      cudaEventCreateWithFlags(e, cudaEventDisableTiming);
   }
   return s;
 }
 
-// The launch sequence on (main, side); called directly or under stream capture.
+// The launch sequence on (main, near, side); called directly or under stream capture.
 static int enqueue(int Npad, int S, double* A, double* W, int* info, Streams& ss) {
   const int nblk = Npad / NB;
   const long as = (long)Npad * Npad, ws = (long)nblk * WD;
@@ -187,14 +271,21 @@ static int enqueue(int Npad, int S, double* A, double* W, int* info, Streams& ss
   if (!attr) {
     cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
     cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+    cudaFuncSetAttribute(diag_block_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(double) * 2 * 32 * (DBU_MAXK + 4)));
     attr = true;
   }
-  cudaStream_t m = ss.main, sd = ss.side;
-  bool side_used = false;
-  // Block columns in PAIRS (j, j+1).  Main stream (the spine): diag j, panel j, rank-128 update of column j+1, diag j+1,
-  // panel j+1, then the look-ahead: the rank-256 update of the NEXT pair's two columns.  Side stream: the rank-256 update
-  // of everything to the right of the next pair, overlapped with the next pair's spine.  Rank 256 halves the read-modify-
-  // write traffic of the trailing matrix per flop.
+  const size_t dbu_smem = sizeof(double) * 2 * 32 * (DBU_MAXK + 4);
+  cudaStream_t m = ss.main, nr = ss.near, sd = ss.side;
+  // Block columns in PAIRS (j, j+1), three streams.  Only what the NEXT diagonal block needs stays on the spine:
+  //   main (urgent): diag j, panel j, the 128 x 128 update of block (j+1, j+1), diag j+1, panel j+1, the 128 x 128 rank-256
+  //                  update of block (j+2, j+2) -- then straight on to diag j+2;
+  //   near (urgent): the rest of column j+1 (needed by panel j+1) while diag j+1 runs, and the rest of the look-ahead -- columns
+  //                  j+2, j+3 below block j+2 (needed by panel j+2 and block (j+3, j+3)) -- while diag j+2 runs;
+  //   side (background): the rank-256 update of everything to the right of the next pair.
+  // A single matrix is bound by this spine, not by flops (22.9 Gflop at N = 4096 would take 0.6 ms at the DMMA peak), so
+  // every microsecond moved from main to near shortens the factorisation; the urgent streams win the SMs when the
+  // background update holds them.
   auto gemm_args = [&](int jcol, int K, int row_blk, int col_blk, int tri) {
     GemmArgs g{};
     g.A = A + (long)jcol * NB; g.lda = Npad; g.a_stride = as;
@@ -203,35 +294,64 @@ static int enqueue(int Npad, int S, double* A, double* W, int* info, Streams& ss
     g.K = K; g.row0 = row_blk * NB; g.col0 = col_blk * NB; g.sub = 1; g.tri = tri;
     return g;
   };
-  for (int j = 0, pair = 0; j < nblk; j += 2, ++pair) {
+  bool near_pending_col = false, near_pending_la = false, near_pending_la2 = false, side_used = false, near_used = false;
+  const int bg_ctas = std::max(num_sms() - std::min(16, std::max(4, S)), 1);   // SMs left free: one per diagonal CTA
+  for (int j = 0; j < nblk; j += 2) {
     diag_kernel<<<S, 256, dsm, m>>>(Npad, j, A, as, W, ws, info);
     count_launch();
-    const int rem = nblk - j - 1;                // block rows below column j
+    const int rem = nblk - j - 1;                // block rows below block j
     if (rem <= 0) break;
+    if (near_pending_la) { cudaStreamWaitEvent(m, ss.larest, 0); near_pending_la = false; }   // column j below the diagonal is up to date
     panel_kernel<<<dim3(rem * 4, 1, S), 256, psm, m>>>(Npad, j, A, as, W, ws);           // L_Ij = A_Ij L_jj^-T
-    launch_gemm<32>(gemm_args(j, NB, j + 1, j + 1, 0), rem * 4, 1, S, m);                 // column j+1 -= L_Ij L_(j+1)j^T
-    diag_kernel<<<S, 256, dsm, m>>>(Npad, j + 1, A, as, W, ws, info);
-    count_launch(3);
-    const int rem2 = nblk - j - 2;               // block rows below column j+1
-    if (rem2 <= 0) break;
-    panel_kernel<<<dim3(rem2 * 4, 1, S), 256, psm, m>>>(Npad, j + 1, A, as, W, ws);
-    cudaEventRecord(ss.panel[pair & 1], m);
-    // look-ahead: the next pair's columns (j+2, j+3) with respect to panels j and j+1; the side stream's update of the
-    // previous pair also wrote those columns, so wait for it first
-    if (side_used) cudaStreamWaitEvent(m, ss.rest[(pair - 1) & 1], 0);
-    launch_gemm<32>(gemm_args(j, 2 * NB, j + 2, j + 2, 1), rem2 * 4, rem2 >= 2 ? 2 : 1, S, m);
+    if (near_pending_la2) { cudaStreamWaitEvent(m, ss.larest2, 0); near_pending_la2 = false; }  // column j+1 carries the look-ahead
+    diag_block_update_kernel<<<dim3(10, S), 256, dbu_smem, m>>>(Npad, j + 1, j * NB, NB, A, as);   // block (j+1, j+1) -= L L^T
     count_launch(2);
-    if (rem2 > 2) {                              // everything to the right of the next pair, on the side stream
-      cudaStreamWaitEvent(sd, ss.panel[pair & 1], 0);
-      launch_gemm<128>(gemm_args(j, 2 * NB, j + 4, j + 4, 1), rem2 - 2, rem2 - 2, S, sd);
-      cudaEventRecord(ss.rest[pair & 1], sd);
+    if (rem > 1) {                               // rest of column j+1, next to diag j+1
+      cudaEventRecord(ss.diagblk, m);
+      cudaStreamWaitEvent(nr, ss.diagblk, 0);
+      launch_gemm<32>(gemm_args(j, NB, j + 2, j + 1, 0), (rem - 1) * 4, 1, S, nr);
+      cudaEventRecord(ss.col, nr);
+      count_launch();
+      near_pending_col = near_used = true;
+    }
+    diag_kernel<<<S, 256, dsm, m>>>(Npad, j + 1, A, as, W, ws, info);
+    count_launch();
+    const int rem2 = nblk - j - 2;               // block rows below block j+1
+    if (rem2 <= 0) break;
+    if (near_pending_col) { cudaStreamWaitEvent(m, ss.col, 0); near_pending_col = false; }
+    panel_kernel<<<dim3(rem2 * 4, 1, S), 256, psm, m>>>(Npad, j + 1, A, as, W, ws);
+    cudaEventRecord(ss.panel, m);
+    count_launch();
+    // look-ahead: the next pair's columns (j+2, j+3) with respect to panels j and j+1; the side stream's update for the
+    // previous pair also wrote those columns, so wait for it first
+    if (side_used) cudaStreamWaitEvent(m, ss.rest, 0);
+    diag_block_update_kernel<<<dim3(10, S), 256, dbu_smem, m>>>(Npad, j + 2, j * NB, 2 * NB, A, as);   // block (j+2, j+2)
+    count_launch();
+    if (rem2 > 1) {                              // columns j+2, j+3 below block j+2: column j+2 first -- panel j+2 waits for it
+      cudaEventRecord(ss.la, m);                 // right after diag j+2 (31 us); column j+3 is not read before block (j+3, j+3)
+      cudaStreamWaitEvent(nr, ss.la, 0);
+      launch_gemm<32>(gemm_args(j, 2 * NB, j + 3, j + 2, 0), (rem2 - 1) * 4, 1, S, nr);
+      cudaEventRecord(ss.larest, nr);
+      launch_gemm<32>(gemm_args(j, 2 * NB, j + 3, j + 3, 1), (rem2 - 1) * 4, 1, S, nr);
+      cudaEventRecord(ss.larest2, nr);
+      count_launch(2);
+      near_pending_la = near_pending_la2 = near_used = true;
+    }
+    if (rem2 > 2) {                              // everything to the right of the next pair, in the background
+      cudaStreamWaitEvent(sd, ss.panel, 0);
+      launch_gemm_background(gemm_args(j, 2 * NB, j + 4, j + 4, 1), rem2 - 2, S, bg_ctas, sd);
+      cudaEventRecord(ss.rest, sd);
       count_launch();
       side_used = true;
     }
   }
+  if (near_used) {
+    cudaEventRecord(ss.join_near, nr);
+    cudaStreamWaitEvent(m, ss.join_near, 0);
+  }
   if (side_used) {
-    cudaEventRecord(ss.join, sd);
-    cudaStreamWaitEvent(m, ss.join, 0);
+    cudaEventRecord(ss.join_side, sd);
+    cudaStreamWaitEvent(m, ss.join_side, 0);
   }
   return 0;
 }

@@ -89,11 +89,11 @@ void run(const char* name) {
   cudaMemcpyFromSymbol(tl, g_diag_tl, sizeof(tl));
   printf("%s NB=%d: diag %.1f us, winv %.1f us, panel(2 CTAs) %.1f us (%s)  max|dL| %.2e  max|WL - I| %.2e  max|X L^T - A| %.2e\n",
          name, NB, best * 1e3, bw * 1e3, bp * 1e3, cudaGetErrorString(err), eL, eW, eX);
-  printf("   load %lld", tl[1] - tl[0]);
-  for (int p = 0; p < NB / 32; ++p) {
-    long long t0 = p ? tl[4 * p] : tl[1];
-    printf(" | p%d chol %lld", p, tl[2 + 4 * p] - t0);
-    if (p + 1 < NB / 32) printf(" subst %lld update %lld", tl[3 + 4 * p] - tl[2 + 4 * p], tl[4 + 4 * p] - tl[3 + 4 * p]);
+  printf("   load %lld | chol0 %lld", tl[1] - tl[0], tl[2] - tl[1]);
+  for (int p = 0; p + 1 < NB / 32; ++p) {
+    long long t0 = p ? tl[6 + 4 * (p - 1)] : tl[2];
+    printf(" | p%d subst %lld tile %lld chol%d %lld (+wait %lld)", p, tl[3 + 4 * p] - t0, tl[4 + 4 * p] - tl[3 + 4 * p], p + 1,
+           tl[5 + 4 * p] - tl[4 + 4 * p], tl[6 + 4 * p] - tl[5 + 4 * p]);
   }
   printf(" | Wdiag %lld store %lld | total %lld cycles\n", tl[21] - tl[20], tl[22] - tl[21], tl[22] - tl[0]);
 }
