@@ -62,6 +62,12 @@ int smk_cov_build_f32(int kind, int N, int M, int D, int S, const float* X, cons
 int smk_cov_build_f64(int kind, int N, int M, int D, int S, const double* X, const double* Y,
                       const double* inv_ls, const double* amp2, const double* diag_add,
                       double* out, int ld, void* stream);
+/* Self case for a consumer that reads the lower triangle only (the Cholesky inside every slice-sampler log-probability,
+ * OPT:637, 659, 690): 32 x 32 tiles strictly above the diagonal are skipped and left as they were.                  */
+int smk_cov_build_lower_f32(int kind, int N, int D, int S, const float* X, const float* inv_ls, const float* amp2,
+                            const float* diag_add, float* out, int ld, void* stream);
+int smk_cov_build_lower_f64(int kind, int N, int D, int S, const double* X, const double* inv_ls, const double* amp2,
+                            const double* diag_add, double* out, int ld, void* stream);
 
 /* ---- (2) batched lower Cholesky: spla.cholesky(., lower=True)  (OPT:540, 567, 585)
  * A: [S][Npad][Npad] in/out (lower triangle is read and overwritten with L; the strict upper

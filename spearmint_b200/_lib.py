@@ -75,6 +75,7 @@ for _t in ("f32", "f64"):
         "smk_sobol_generate_" + _t: ([_i, _ll, _ll, _p, _p, _p], _i),
         "smk_mll_grad_terms_" + _t: ([_i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p], _i),
         "smk_cov_build_" + _t: ([_i] * 5 + [_p] * 6 + [_i, _p], _i),
+        "smk_cov_build_lower_" + _t: ([_i] * 4 + [_p] * 5 + [_i, _p], _i),
         "smk_potrf_lower_batched_" + _t: ([_i, _i, _p, _p, _p, _p], _i),
         "smk_chol_solve_" + _t: ([_i] * 4 + [_p, _p, _p, _ll, _i, _p, _p, _p, _p, _p], _i),
         "smk_loglik_set_rhs_" + _t: ([_i, _i, _i, _p, _p, _p, _p], _i),

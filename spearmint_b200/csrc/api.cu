@@ -47,7 +47,7 @@ int check_launch(const char* what) {
 
 // implemented in the other translation units
 template <typename T>
-int cov_build(int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, T*, int, cudaStream_t);
+int cov_build(int, int, int, int, int, const T*, const T*, const T*, const T*, const T*, T*, int, cudaStream_t, int lower = 0);
 template <typename T>
 int potrf_lower_batched(int, int, T*, T*, int*, cudaStream_t);
 template <typename T>
@@ -138,6 +138,14 @@ int smk_cov_build_f32(int kind, int N, int M, int D, int S, const float* X, cons
 int smk_cov_build_f64(int kind, int N, int M, int D, int S, const double* X, const double* Y, const double* inv_ls,
                       const double* amp2, const double* diag_add, double* out, int ld, void* stream) {
   return cov_build<double>(kind, N, M, D, S, X, Y, inv_ls, amp2, diag_add, out, ld, ST(stream));
+}
+int smk_cov_build_lower_f32(int kind, int N, int D, int S, const float* X, const float* inv_ls, const float* amp2,
+                            const float* diag_add, float* out, int ld, void* stream) {
+  return cov_build<float>(kind, N, N, D, S, X, nullptr, inv_ls, amp2, diag_add, out, ld, ST(stream), 1);
+}
+int smk_cov_build_lower_f64(int kind, int N, int D, int S, const double* X, const double* inv_ls, const double* amp2,
+                            const double* diag_add, double* out, int ld, void* stream) {
+  return cov_build<double>(kind, N, N, D, S, X, nullptr, inv_ls, amp2, diag_add, out, ld, ST(stream), 1);
 }
 
 int smk_potrf_lower_batched_f32(int Npad, int S, float* A, float* winv, int* info, void* stream) {

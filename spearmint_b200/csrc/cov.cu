@@ -17,7 +17,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) cov_build_kernel(int kind, int N, int M, int D, const T* __restrict__ X,
                                                          const T* __restrict__ Y, const T* __restrict__ inv_ls,
                                                          const T* __restrict__ amp2, const T* __restrict__ diag_add,
-                                                         T* __restrict__ out, int ld, int self) {
+                                                         T* __restrict__ out, int ld, int self, int lower) {
+  if (lower && blockIdx.x > blockIdx.y) return;            // tile strictly above the diagonal: the factorisations never read it
   __shared__ T xs[kCT][kDC + 1];
   __shared__ T ys[kCT][kDC + 1];
   const int s = blockIdx.z;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int kind, int N, int M, 
 
 template <typename T>
 int cov_build(int kind, int N, int M, int D, int S, const T* X, const T* Y, const T* inv_ls, const T* amp2,
-              const T* diag_add, T* out, int ld, cudaStream_t st) {
+              const T* diag_add, T* out, int ld, cudaStream_t st, int lower) {
   if (kind < 0 || kind > 3) return -1;
   if (N <= 0) return -2;
   if (D <= 0) return -4;
@@ -81,18 +82,19 @@ int cov_build(int kind, int N, int M, int D, int S, const T* X, const T* Y, cons
   if (!amp2) return -9;
   if (!out) return -11;
   const int self = (Y == nullptr);
+  if (lower && !self) return -13;
   if (!self && M <= 0) return -3;
   if (ld < (self ? N : M)) return -12;
   const int rows = self ? ld : N, cols = self ? ld : M;
   dim3 grid((cols + kCT - 1) / kCT, (rows + kCT - 1) / kCT, S);
-  cov_build_kernel<T><<<grid, 256, 0, st>>>(kind, N, M, D, X, Y, inv_ls, amp2, diag_add, out, ld, self);
+  cov_build_kernel<T><<<grid, 256, 0, st>>>(kind, N, M, D, X, Y, inv_ls, amp2, diag_add, out, ld, self, lower);
   count_launch();
   return check_launch("cov_build");
 }
 
 template int cov_build<float>(int, int, int, int, int, const float*, const float*, const float*, const float*,
-                              const float*, float*, int, cudaStream_t);
+                              const float*, float*, int, cudaStream_t, int);
 template int cov_build<double>(int, int, int, int, int, const double*, const double*, const double*,
-                               const double*, const double*, double*, int, cudaStream_t);
+                               const double*, const double*, double*, int, cudaStream_t, int);
 
 }  // namespace smk

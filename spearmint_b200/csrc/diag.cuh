@@ -313,7 +313,8 @@ __device__ __forceinline__ void diag_update(float* a, int p, int part) {
 // is left untouched).  wd: [NB/32][32][32] receives the inverses of the 32 x 32 diagonal pieces of L_jj.
 // info (may be NULL): 1-based index of the first non-positive pivot, written once.
 template <typename T, int NB>
-__device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ wd, int* info, int info_base, T* sm) {
+__device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ wd, int* info, int info_base, T* sm,
+                                  bool trigger = false) {
   using DS = DiagSmem<T, NB>;
   constexpr int SB = 32, LDT = DS::LDT, NP = DS::NP, TILE = DS::TILE;
   T* a = sm;
@@ -395,6 +396,9 @@ __device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ wd
     DIAG_STAMP(6 + 4 * p);
   }
   DIAG_STAMP(20);
+  // programmatic dependent launch (potrf_ll): let the panel's CTAs come up while the inverses are formed and stored;
+  // they wait (griddepcontrol.wait) for this grid to finish before they read anything
+  if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- inverses of the diagonal pieces, one warp each
   if (warp < NP) warp_trinv32<T>(w + warp * TILE, ipv + warp * SB, w + warp * TILE, lane);
@@ -429,7 +433,7 @@ struct PanelSmem {
 
 template <typename T, int NB>
 __device__ void panel_sub_block(T* __restrict__ Ap, int ld, const T* __restrict__ Ljj, const T* __restrict__ wd,
-                                T* __restrict__ hi, T* __restrict__ lo, T* sm) {
+                                T* __restrict__ hi, T* __restrict__ lo, T* sm, bool trigger = false) {
   using PS = PanelSmem<T, NB>;
   constexpr int SB = 32, LDT = PS::LDT, NP = PS::NP, TILE = PS::TILE;
   T* lt = sm;                               // off-diagonal tile (pi, pj), pj < pi, at index pi (pi - 1) / 2 + pj
@@ -506,6 +510,7 @@ __device__ void panel_sub_block(T* __restrict__ Ap, int ld, const T* __restrict_
       }
     __syncthreads();
   }
+  if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int e = tid; e < SB * NB; e += 256) {
     const int i = e / NB, k = e % NB;
     const T x = xt[(k >> 5) * TILE + i * LDT + (k & 31)];

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 
@@ -34,24 +35,32 @@ constexpr int STAGES = 3;
 
 constexpr int WD = NB * 32;     // compact diagonal inverses of one block: [4][32][32]
 
+// Programmatic dependent launch along the spine (diag -> panel -> block update -> diag ...): a kernel launched with the
+// attribute may start while its predecessor in the stream is still running (after the predecessor's launch_dependents);
+// nothing of the predecessor's output is touched before this wait.  Without the attribute the wait returns at once.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __global__ void __launch_bounds__(256) diag_kernel(int ld, int jb, double* __restrict__ A, long a_stride,
                                                     double* __restrict__ W, long w_stride, int* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.x;
   double* Ab = A + (long)s * a_stride + (long)jb * NB * ld + (long)jb * NB;
+  pdl_wait();
   diag_factor_block<double, NB>(Ab, ld, W + (long)s * w_stride + (long)jb * WD, info ? info + s : nullptr, jb * NB,
-                                reinterpret_cast<double*>(smem_raw));
+                                reinterpret_cast<double*>(smem_raw), true);
 }
 
-// L_Ij = A_Ij L_jj^-T by block substitution, 32 rows per CTA; grid = (rows below / 32, 1, S)
-__global__ void __launch_bounds__(256) panel_kernel(int ld, int jb, double* __restrict__ A, long a_stride,
+// L_Ij = A_Ij L_jj^-T by block substitution, 32 rows per CTA, block rows row_blk0, row_blk0 + 1, ...; grid = (rows / 32, 1, S)
+__global__ void __launch_bounds__(256) panel_kernel(int ld, int jb, int row_blk0, double* __restrict__ A, long a_stride,
                                                      const double* __restrict__ W, long w_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int s = blockIdx.z;
   double* As = A + (long)s * a_stride;
-  panel_sub_block<double, NB>(As + ((long)(jb + 1) * NB + (long)blockIdx.x * 32) * ld + (long)jb * NB, ld,
+  pdl_wait();
+  panel_sub_block<double, NB>(As + ((long)row_blk0 * NB + (long)blockIdx.x * 32) * ld + (long)jb * NB, ld,
                               As + (long)jb * NB * ld + (long)jb * NB, W + (long)s * w_stride + (long)jb * WD, nullptr,
-                              nullptr, reinterpret_cast<double*>(smem_raw));
+                              nullptr, reinterpret_cast<double*>(smem_raw), true);
 }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -184,6 +193,8 @@ __global__ void __launch_bounds__(256) diag_block_update_kernel(int ld, int b, i
   const double* pa = As + ((long)b * NB + ti * 32) * ld + k0;
   const double* pb = As + ((long)b * NB + tj * 32) * ld + k0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+  pdl_wait();
+  pdl_trigger();                                     // the diagonal kernel behind this one is a single CTA per matrix
   const int cpr = K / 2;                             // 16-byte chunks per row
   for (int ch = tid; ch < 32 * cpr; ch += 256) {
     const int row = ch / cpr, pc = ch - row * cpr;
@@ -230,8 +241,8 @@ static void launch_gemm(const GemmArgs& g, int tiles_m, int tiles_n, int S, cuda
 //   * ctas < number of SMs: the diagonal kernel (186 registers x 256 threads) cannot share an SM with this kernel, and a
 //     tile of it runs ~45 us -- launched over all SMs it made every diagonal block wait for a tile to drain;
 //   * a 2-stage ring (82 KB): the panel kernel (138 KB) and the 32-row GEMMs (77 KB) fit beside it on the same SM.
-static void launch_gemm_background(GemmArgs g, int nt, int S, int ctas, cudaStream_t st) {
-  constexpr int ST = 2;
+template <int ST>
+static void launch_gemm_background_st(GemmArgs g, int nt, int S, int ctas, cudaStream_t st) {
   const size_t smem = sizeof(double) * ST * (128 + 128) * LDS;
   static bool attr = false;
   if (!attr) {
@@ -242,10 +253,30 @@ static void launch_gemm_background(GemmArgs g, int nt, int S, int ctas, cudaStre
   const long items = (long)S * nt * (nt + 1) / 2;
   dgemm_nt_kernel<128, ST><<<(unsigned)std::min<long>(items, ctas), 256, smem, st>>>(g);
 }
+static void launch_gemm_background(const GemmArgs& g, int nt, int S, int ctas, cudaStream_t st) {
+  static int stages = -1;
+  if (stages < 0) { const char* e = getenv("SMK_LL_BG_STAGES"); stages = (e && e[0] == '3') ? 3 : 2; }
+  if (stages == 3) launch_gemm_background_st<3>(g, nt, S, ctas, st);
+  else launch_gemm_background_st<2>(g, nt, S, ctas, st);
+}
+
+// kernel launch on the spine: programmatic stream serialization unless SMK_LL_PDL=0
+template <typename... KArgs, typename... Args>
+static void launch_spine(void (*kern)(KArgs...), dim3 grid, size_t smem, cudaStream_t st, Args... args) {
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("SMK_LL_PDL"); pdl = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 struct Streams {
   cudaStream_t main = nullptr, near = nullptr, side = nullptr;
-  cudaEvent_t diagblk = nullptr, col = nullptr, la = nullptr, larest = nullptr, larest2 = nullptr, panel = nullptr, rest = nullptr,
+  cudaEvent_t diag0 = nullptr, diag1 = nullptr, head0 = nullptr, col = nullptr, la = nullptr, larest = nullptr, larest2 = nullptr, panel = nullptr, rest = nullptr,
               join_near = nullptr, join_side = nullptr;
 };
 static Streams& streams() {
@@ -256,7 +287,7 @@ static Streams& streams() {
     cudaStreamCreateWithPriority(&s.main, cudaStreamNonBlocking, hi);
     cudaStreamCreateWithPriority(&s.near, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi);   // the diagonal kernel needs an EMPTY SM: it goes first
     cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, lo);
-    for (cudaEvent_t* e : {&s.diagblk, &s.col, &s.la, &s.larest, &s.larest2, &s.panel, &s.rest, &s.join_near, &s.join_side})
+    for (cudaEvent_t* e : {&s.diag0, &s.diag1, &s.head0, &s.col, &s.la, &s.larest, &s.larest2, &s.panel, &s.rest, &s.join_near, &s.join_side})
       cudaEventCreateWithFlags(e, cudaEventDisableTiming);
   }
   return s;
@@ -277,15 +308,15 @@ static int enqueue(int Npad, int S, double* A, double* W, int* info, Streams& ss
   }
   const size_t dbu_smem = sizeof(double) * 2 * 32 * (DBU_MAXK + 4);
   cudaStream_t m = ss.main, nr = ss.near, sd = ss.side;
-  // Block columns in PAIRS (j, j+1), three streams.  Only what the NEXT diagonal block needs stays on the spine:
-  //   main (urgent): diag j, panel j, the 128 x 128 update of block (j+1, j+1), diag j+1, panel j+1, the 128 x 128 rank-256
-  //                  update of block (j+2, j+2) -- then straight on to diag j+2;
-  //   near (urgent): the rest of column j+1 (needed by panel j+1) while diag j+1 runs, and the rest of the look-ahead -- columns
-  //                  j+2, j+3 below block j+2 (needed by panel j+2 and block (j+3, j+3)) -- while diag j+2 runs;
+  // Block columns in PAIRS (j, j+1), three streams.  Only what the NEXT diagonal block needs stays on the spine, and the
+  // spine's kernels are small enough (1, 4 and 10 CTAs per matrix) to run on the SMs the background update leaves free --
+  // next to a background CTA they share the SM's float64 pipe and take twice as long:
+  //   main (urgent): diag j, panel HEAD j (the 128 rows of block row j+1), update of block (j+1, j+1), diag j+1, panel head
+  //                  j+1 (block row j+2), rank-256 update of block (j+2, j+2) -- then straight on to diag j+2;
+  //   near (urgent): everything else of the two block columns while the diagonal kernels run: panel rest j, rest of column
+  //                  j+1, panel rest j+1, then the look-ahead columns j+2 (panel head j+2 waits for it) and j+3;
   //   side (background): the rank-256 update of everything to the right of the next pair.
-  // A single matrix is bound by this spine, not by flops (22.9 Gflop at N = 4096 would take 0.6 ms at the DMMA peak), so
-  // every microsecond moved from main to near shortens the factorisation; the urgent streams win the SMs when the
-  // background update holds them.
+  // A single matrix is bound by this spine, not by flops (22.9 Gflop at N = 4096 would take 0.6 ms at the DMMA peak).
   auto gemm_args = [&](int jcol, int K, int row_blk, int col_blk, int tri) {
     GemmArgs g{};
     g.A = A + (long)jcol * NB; g.lda = Npad; g.a_stride = as;
@@ -294,51 +325,66 @@ static int enqueue(int Npad, int S, double* A, double* W, int* info, Streams& ss
     g.K = K; g.row0 = row_blk * NB; g.col0 = col_blk * NB; g.sub = 1; g.tri = tri;
     return g;
   };
-  bool near_pending_col = false, near_pending_la = false, near_pending_la2 = false, side_used = false, near_used = false;
-  const int bg_ctas = std::max(num_sms() - std::min(16, std::max(4, S)), 1);   // SMs left free: one per diagonal CTA
+  bool pend_col = false, pend_la = false, pend_la2 = false, side_used = false, near_used = false;
+  const int reserve = std::min(24, std::max(8, 10 * S + 2));          // the widest spine kernel: 10 CTAs per matrix
+  const int bg_ctas = std::max(num_sms() - reserve, 1);
+  const double* Wc = W;
   for (int j = 0; j < nblk; j += 2) {
-    diag_kernel<<<S, 256, dsm, m>>>(Npad, j, A, as, W, ws, info);
+    launch_spine(diag_kernel, dim3(S), dsm, m, Npad, j, A, as, W, ws, info);
     count_launch();
     const int rem = nblk - j - 1;                // block rows below block j
     if (rem <= 0) break;
-    if (near_pending_la) { cudaStreamWaitEvent(m, ss.larest, 0); near_pending_la = false; }   // column j below the diagonal is up to date
-    panel_kernel<<<dim3(rem * 4, 1, S), 256, psm, m>>>(Npad, j, A, as, W, ws);           // L_Ij = A_Ij L_jj^-T
-    if (near_pending_la2) { cudaStreamWaitEvent(m, ss.larest2, 0); near_pending_la2 = false; }  // column j+1 carries the look-ahead
-    diag_block_update_kernel<<<dim3(10, S), 256, dbu_smem, m>>>(Npad, j + 1, j * NB, NB, A, as);   // block (j+1, j+1) -= L L^T
+    if (pend_la) { cudaStreamWaitEvent(m, ss.larest, 0); pend_la = false; }     // column j below the diagonal is up to date
+    if (rem > 1) {                               // panel rest j next to the head: rows from block j+2 on
+      cudaEventRecord(ss.diag0, m);
+      cudaStreamWaitEvent(nr, ss.diag0, 0);
+      panel_kernel<<<dim3((rem - 1) * 4, 1, S), 256, psm, nr>>>(Npad, j, j + 2, A, as, Wc, ws);
+      count_launch();
+      near_used = true;
+    }
+    launch_spine(panel_kernel, dim3(4, 1, S), psm, m, Npad, j, j + 1, A, as, Wc, ws);          // head: L_(j+1)j
+    if (pend_la2) { cudaStreamWaitEvent(m, ss.larest2, 0); pend_la2 = false; }   // block (j+1, j+1) carries the look-ahead
+    launch_spine(diag_block_update_kernel, dim3(10, S), dbu_smem, m, Npad, j + 1, j * NB, NB, A, as);   // block (j+1, j+1) -= L L^T
     count_launch(2);
-    if (rem > 1) {                               // rest of column j+1, next to diag j+1
-      cudaEventRecord(ss.diagblk, m);
-      cudaStreamWaitEvent(nr, ss.diagblk, 0);
+    if (rem > 1) {                               // rest of column j+1 (needs L_(j+1)j and panel rest j), next to diag j+1
+      cudaEventRecord(ss.head0, m);
+      cudaStreamWaitEvent(nr, ss.head0, 0);
       launch_gemm<32>(gemm_args(j, NB, j + 2, j + 1, 0), (rem - 1) * 4, 1, S, nr);
       cudaEventRecord(ss.col, nr);
       count_launch();
-      near_pending_col = near_used = true;
+      pend_col = true;
     }
-    diag_kernel<<<S, 256, dsm, m>>>(Npad, j + 1, A, as, W, ws, info);
+    launch_spine(diag_kernel, dim3(S), dsm, m, Npad, j + 1, A, as, W, ws, info);
     count_launch();
     const int rem2 = nblk - j - 2;               // block rows below block j+1
     if (rem2 <= 0) break;
-    if (near_pending_col) { cudaStreamWaitEvent(m, ss.col, 0); near_pending_col = false; }
-    panel_kernel<<<dim3(rem2 * 4, 1, S), 256, psm, m>>>(Npad, j + 1, A, as, W, ws);
-    cudaEventRecord(ss.panel, m);
+    if (rem2 > 1) {                              // panel rest j+1: rows from block j+3 on (column j+1 there: ss.col, same stream)
+      cudaEventRecord(ss.diag1, m);
+      cudaStreamWaitEvent(nr, ss.diag1, 0);
+      panel_kernel<<<dim3((rem2 - 1) * 4, 1, S), 256, psm, nr>>>(Npad, j + 1, j + 3, A, as, Wc, ws);
+      cudaEventRecord(ss.panel, nr);
+      count_launch();
+    }
+    if (pend_col) { cudaStreamWaitEvent(m, ss.col, 0); pend_col = false; }       // column j+1 (and panel rest j) complete
+    launch_spine(panel_kernel, dim3(4, 1, S), psm, m, Npad, j + 1, j + 2, A, as, Wc, ws);      // head: L_(j+2)(j+1)
     count_launch();
     // look-ahead: the next pair's columns (j+2, j+3) with respect to panels j and j+1; the side stream's update for the
     // previous pair also wrote those columns, so wait for it first
     if (side_used) cudaStreamWaitEvent(m, ss.rest, 0);
-    diag_block_update_kernel<<<dim3(10, S), 256, dbu_smem, m>>>(Npad, j + 2, j * NB, 2 * NB, A, as);   // block (j+2, j+2)
+    launch_spine(diag_block_update_kernel, dim3(10, S), dbu_smem, m, Npad, j + 2, j * NB, 2 * NB, A, as);   // block (j+2, j+2)
     count_launch();
     if (rem2 > 1) {                              // columns j+2, j+3 below block j+2: column j+2 first -- panel j+2 waits for it
-      cudaEventRecord(ss.la, m);                 // right after diag j+2 (31 us); column j+3 is not read before block (j+3, j+3)
+      cudaEventRecord(ss.la, m);                 // (orders them behind the previous pair's background update as well)
       cudaStreamWaitEvent(nr, ss.la, 0);
       launch_gemm<32>(gemm_args(j, 2 * NB, j + 3, j + 2, 0), (rem2 - 1) * 4, 1, S, nr);
       cudaEventRecord(ss.larest, nr);
       launch_gemm<32>(gemm_args(j, 2 * NB, j + 3, j + 3, 1), (rem2 - 1) * 4, 1, S, nr);
       cudaEventRecord(ss.larest2, nr);
       count_launch(2);
-      near_pending_la = near_pending_la2 = near_used = true;
+      pend_la = pend_la2 = true;
     }
     if (rem2 > 2) {                              // everything to the right of the next pair, in the background
-      cudaStreamWaitEvent(sd, ss.panel, 0);
+      cudaStreamWaitEvent(sd, ss.panel, 0);      // both panels down to the last row
       launch_gemm_background(gemm_args(j, 2 * NB, j + 4, j + 4, 1), rem2 - 2, S, bg_ctas, sd);
       cudaEventRecord(ss.rest, sd);
       count_launch();

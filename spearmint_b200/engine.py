@@ -805,7 +805,8 @@ class LogLik(object):
         # and shrink proposals follow in pairs once the interval is final
         self.speculate = (3, 0) if self.N <= 1536 else (0, 2)
         dt, dev = eng.dtype, eng.device
-        self.L = torch.empty((max_batch, self.Npad, self.Npad), dtype=dt, device=dev)
+        # zeros once: the covariance is rebuilt in the lower triangle only (smk_cov_build_lower), the rest is never read
+        self.L = torch.zeros((max_batch, self.Npad, self.Npad), dtype=dt, device=dev)
         # float64: dedicated look-ahead / DMMA factorisation (csrc/potrf_ll.cu); its workspace holds the inverse diagonal
         # blocks.  float32 (tests only): the generic blocked factorisation.
         self.fast = (dt == torch.float64) and os.environ.get("SMK_LOGLIK_IMPL", "ll") == "ll"
@@ -829,8 +830,8 @@ class LogLik(object):
             B = len(hs)
             hb = eng.hypers([(h[0], h[1], h[2], np.asarray(h[3], dtype=float)) for h in hs], self.kind)
             st = eng.stream()
-            check(fn("smk_cov_build", dt)(KINDS[self.kind], N, N, self.D, B, ptr(self.X), None, ptr(hb.inv_ls),
-                                          ptr(hb.amp2), ptr(hb.noise), ptr(self.L), Npad, st), "cov_build")
+            check(fn("smk_cov_build_lower", dt)(KINDS[self.kind], N, self.D, B, ptr(self.X), ptr(hb.inv_ls),
+                                                ptr(hb.amp2), ptr(hb.noise), ptr(self.L), Npad, st), "cov_build")
             check(fn("smk_loglik_set_rhs", dt)(N, Npad, B, ptr(self.y), ptr(hb.mean), ptr(self.L), st), "loglik_set_rhs")
             if self.fast:
                 check(_lib.lib().smk_potrf_loglik_f64(Npad, B, ptr(self.L), ptr(self.winv), self.ws_bytes, ptr(self.info),

@@ -41,6 +41,32 @@ def test_cov_build(engines, kind, prec):
         np.testing.assert_allclose(Kc[s], O.cov(kind, h[2], h[3], X, Cd), **tol)
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_cov_build_lower(engines, prec):
+    """smk_cov_build_lower: the lower triangle (and the padded identity) bit-equal to the full build, the 32 x 32 tiles
+    strictly above the diagonal left exactly as they were."""
+    import torch
+    from spearmint_b200.engine import KINDS as KIDS, check, fn, ptr
+    eng = engines[prec]
+    dt = eng.dtype
+    N, D, S, ld = 150, 5, 2, 256
+    X, Cd, y, hs = _problem(D, N, 4, S, 9)
+    hb = eng.hypers(hs, "Matern52")
+    Xd = eng.to_dev(X)
+    full = torch.zeros((S, ld, ld), dtype=dt, device=eng.device)
+    low = torch.full((S, ld, ld), -7.0, dtype=dt, device=eng.device)
+    st = eng.stream()
+    check(fn("smk_cov_build", dt)(KIDS["Matern52"], N, N, D, S, ptr(Xd), None, ptr(hb.inv_ls), ptr(hb.amp2), ptr(hb.noise),
+                                  ptr(full), ld, st), "cov_build")
+    check(fn("smk_cov_build_lower", dt)(KIDS["Matern52"], N, D, S, ptr(Xd), ptr(hb.inv_ls), ptr(hb.amp2), ptr(hb.noise),
+                                        ptr(low), ld, st), "cov_build_lower")
+    full, low = full.cpu().numpy(), low.cpu().numpy()
+    ti, tj = np.arange(ld)[:, None] // 32, np.arange(ld)[None, :] // 32
+    for s in range(S):
+        assert np.array_equal(low[s][ti >= tj], full[s][ti >= tj])
+        assert np.all(low[s][ti < tj] == -7.0)
+
+
 @pytest.mark.parametrize("prec,N", [("f64", 64), ("f64", 200), ("f32", 128), ("f32", 300), ("f32", 700)])
 def test_potrf_and_solve(engines, prec, N):
     import torch

@@ -34,8 +34,8 @@ for _ in range(reps):
     st = eng.stream()
     t1 = time.perf_counter()
     ev[0].record()
-    check(fn("smk_cov_build", dt)(KINDS[ll.kind], N, N, D, B, ptr(ll.X), None, ptr(hb.inv_ls), ptr(hb.amp2), ptr(hb.noise),
-                                  ptr(ll.L), Npad, st), "cov_build")
+    check(fn("smk_cov_build_lower", dt)(KINDS[ll.kind], N, D, B, ptr(ll.X), ptr(hb.inv_ls), ptr(hb.amp2), ptr(hb.noise),
+                                        ptr(ll.L), Npad, st), "cov_build")
     check(fn("smk_loglik_set_rhs", dt)(N, Npad, B, ptr(ll.y), ptr(hb.mean), ptr(ll.L), st), "set_rhs")
     ev[1].record()
     check(_lib.lib().smk_potrf_loglik_f64(Npad, B, ptr(ll.L), ptr(ll.winv), ll.ws_bytes, ptr(ll.info), ll.use_graph, st), "potrf")
