@@ -149,6 +149,13 @@ int smk_potrf_lower_batched_tc_f32(int Npad, int S, float* A, float* winv, int* 
 size_t smk_trtri_tc_workspace_bytes(int Npad, int Np, int S);
 int smk_trtri_split_tc_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi,
                            float* linv_lo, void* workspace, size_t workspace_bytes, void* stream);
+/* Both of the above in one call, pipelined: the inverse runs one block step behind the factorisation on an internal second
+ * stream (row block K of L^-1 only needs block column K of L to be final), ordered behind `stream` on entry and joined
+ * back into it on return.  winv receives the full diagonal-block inverses as usual.  potrf_ws: 2*S*Npad*Npad floats;
+ * trtri_ws: smk_trtri_tc_workspace_bytes -- two distinct buffers, both live until the call's work has completed.   */
+int smk_potrf_trtri_tc_f32(int Npad, int Np, int S, float* A, float* winv, int* info, void* potrf_ws,
+                           size_t potrf_ws_bytes, float* linv_hi, float* linv_lo, void* trtri_ws,
+                           size_t trtri_ws_bytes, void* stream);
 /* alpha[s] = K_s^-1 (y - mean[s]) from the explicit inverse (two parallel mat-vecs; OPT:543); tmp: [S][Np] floats. */
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "smk_potrf_lower_batched_tc_f32": ([_i, _i, _p, _p, _p, _p, _sz, _p], _i),
     "smk_trtri_tc_workspace_bytes": ([_i, _i, _i], _sz),
     "smk_trtri_split_tc_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
+    "smk_potrf_trtri_tc_f32": ([_i, _i, _i, _p, _p, _p, _p, _sz, _p, _p, _p, _sz, _p], _i),
     "smk_linv_alpha_f32": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p], _i),
     "smk_kxt_pack_workspace_bytes": ([_i, _i, _i], _sz),
     "smk_debug_kxt_tc_timeline": ([_p, _i], _i),

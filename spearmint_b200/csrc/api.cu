@@ -77,7 +77,8 @@ int tc_np(int);
 size_t trtri_workspace_bytes(int, int);
 int trtri_split(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
 size_t predict_tc_workspace_bytes(int, int, int, int);
-int potrf_lower_batched_tc(int, int, float*, float*, int*, float*, float*, cudaStream_t);
+int potrf_lower_batched_tc(int, int, float*, float*, int*, float*, float*, cudaStream_t, cudaEvent_t* blk_done = nullptr);
+int potrf_trtri_tc(int, int, int, float*, float*, int*, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 size_t trtri_tc_workspace_bytes(int, int, int);
 int trtri_split_tc(int, int, int, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
 int linv_alpha(int, int, int, const float*, const float*, const float*, const float*, float*, int, float*, cudaStream_t);
@@ -220,6 +221,13 @@ size_t smk_trtri_tc_workspace_bytes(int Npad, int Np, int S) { return trtri_tc_w
 int smk_trtri_split_tc_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi, float* linv_lo,
                            void* workspace, size_t workspace_bytes, void* stream) {
   return trtri_split_tc(Npad, Np, S, L, winv, linv_hi, linv_lo, workspace, workspace_bytes, ST(stream));
+}
+int smk_potrf_trtri_tc_f32(int Npad, int Np, int S, float* A, float* winv, int* info, void* potrf_ws, size_t potrf_ws_bytes,
+                           float* linv_hi, float* linv_lo, void* trtri_ws, size_t trtri_ws_bytes, void* stream) {
+  if (!potrf_ws || potrf_ws_bytes < 2 * (size_t)S * Npad * Npad * sizeof(float)) return -8;
+  float* lhi = reinterpret_cast<float*>(potrf_ws);
+  return potrf_trtri_tc(Npad, Np, S, A, winv, info, lhi, lhi + (size_t)S * Npad * Npad, linv_hi, linv_lo, trtri_ws,
+                        trtri_ws_bytes, ST(stream));
 }
 int smk_linv_alpha_f32(int N, int Np, int S, const float* linv_hi, const float* linv_lo, const float* y,
                        const float* mean, float* alpha, int ld_alpha, float* tmp, void* stream) {

@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(int Npad, int jb, T* _
 // ------------------------------------------------------------------------------------------ full inverse blocks
 // W_jj = L_jj^-1 for every diagonal block of every sample at once (grid = (nblk, S)), after the factorisation.
 template <typename T>
-__global__ void __launch_bounds__(256) potrf_winv_kernel(int Npad, const T* __restrict__ A, T* __restrict__ winv) {
+__global__ void __launch_bounds__(256) potrf_winv_kernel(int Npad, const T* __restrict__ A, T* __restrict__ winv, int jb0) {
   constexpr int NB = Cfg<T>::NB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int jb = blockIdx.x, s = blockIdx.y;
+  const int jb = jb0 + blockIdx.x, s = blockIdx.y;
   const T* Ljj = A + (long)s * Npad * Npad + (long)jb * NB * Npad + (long)jb * NB;
   T* Wb = winv + ((long)s * (Npad / NB) + jb) * NB * NB;
   winv_assemble_block<T, NB>(Ljj, Npad, Wb, Wb, reinterpret_cast<T*>(smem_raw));
@@ -134,7 +134,7 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
     potrf_trailing_kernel<T><<<dim3(rem, rem, S), 256, 0, st>>>(Npad, jb, 2, jb + 2, A);   // rank 2*NB, columns >= jb+2
     count_launch(2);
   }
-  potrf_winv_kernel<T><<<dim3(nblk, S), 256, wsm, st>>>(Npad, A, winv);
+  potrf_winv_kernel<T><<<dim3(nblk, S), 256, wsm, st>>>(Npad, A, winv, 0);
   count_launch();
   return check_launch("potrf_lower_batched");
 }
@@ -145,7 +145,11 @@ int potrf_lower_batched(int Npad, int S, T* A, T* winv, int* info, cudaStream_t 
 //   column jb+1 is brought up to date w.r.t. column jb by one rank-NB SIMT update.
 int tc_chol_update(int Npad, int S, int jb, int ncols, float* A, const float* lhi, const float* llo, cudaStream_t st);
 
-int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, float* lhi, float* llo, cudaStream_t st) {
+// blk_done (optional, nblk events): blk_done[j] is recorded on st once block column j is final AND the panel below it has
+// read the compact diagonal inverses (the full W_jj may then overwrite them); with blk_done the full inverses are NOT
+// formed here -- the caller does it per block (potrf_winv_block) as the events fire (potrf_trtri_tc, predict_tc.cu).
+int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, float* lhi, float* llo, cudaStream_t st,
+                           cudaEvent_t* blk_done) {
   constexpr int NB = Cfg<float>::NB;
   if (Npad <= 0 || Npad % kNpadMult) return -1;
   if (S <= 0) return -2;
@@ -154,6 +158,7 @@ int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, fl
   const size_t dsm = DiagSmem<float, NB>::bytes, psm = PanelSmem<float, NB>::bytes, wsm = WinvSmem<float, NB>::bytes;
   potrf_set_attrs<float>();
   cudaMemsetAsync(info, 0, sizeof(int) * S, st);
+  auto done = [&](int j) { if (blk_done) cudaEventRecord(blk_done[j], st); };
   for (int jb = 0; jb < nblk; jb += 2) {
     if (jb > 0) {
       int rc = tc_chol_update(Npad, S, jb, (jb + 1 < nblk) ? 2 * NB : NB, A, lhi, llo, st);
@@ -162,19 +167,30 @@ int potrf_lower_batched_tc(int Npad, int S, float* A, float* winv, int* info, fl
     potrf_diag_kernel<float><<<S, 256, dsm, st>>>(Npad, jb, A, winv, info);
     count_launch();
     int rem = nblk - jb - 1;
-    if (rem <= 0) break;
+    if (rem <= 0) { done(jb); break; }
     potrf_panel_kernel<float><<<dim3(rem * (NB / 32), 1, S), 256, psm, st>>>(Npad, jb, A, winv, lhi, llo);
+    done(jb);
     potrf_trailing_kernel<float><<<dim3(rem, 1, S), 256, 0, st>>>(Npad, jb, 1, jb + 1, A);
     potrf_diag_kernel<float><<<S, 256, dsm, st>>>(Npad, jb + 1, A, winv, info);
     count_launch(3);
     rem = nblk - jb - 2;
-    if (rem <= 0) break;
+    if (rem <= 0) { done(jb + 1); break; }
     potrf_panel_kernel<float><<<dim3(rem * (NB / 32), 1, S), 256, psm, st>>>(Npad, jb + 1, A, winv, lhi, llo);
+    done(jb + 1);
     count_launch();
   }
-  potrf_winv_kernel<float><<<dim3(nblk, S), 256, wsm, st>>>(Npad, A, winv);
-  count_launch();
+  if (!blk_done) {
+    potrf_winv_kernel<float><<<dim3(nblk, S), 256, wsm, st>>>(Npad, A, winv, 0);
+    count_launch();
+  }
   return check_launch("potrf_lower_batched_tc");
+}
+
+// full W_jj of block column jb (all samples): see blk_done above
+void potrf_winv_block(int Npad, int S, int jb, const float* A, float* winv, cudaStream_t st) {
+  potrf_set_attrs<float>();
+  potrf_winv_kernel<float><<<dim3(1, S), 256, WinvSmem<float, Cfg<float>::NB>::bytes, st>>>(Npad, A, winv, jb);
+  count_launch();
 }
 
 template int potrf_lower_batched<float>(int, int, float*, float*, int*, cudaStream_t);

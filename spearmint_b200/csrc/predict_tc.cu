@@ -26,6 +26,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <vector>
 #include <cstdlib>
 #include <cstring>
 
@@ -874,8 +875,13 @@ size_t trtri_tc_workspace_bytes(int Npad, int Np, int S) {
   return (2 * (size_t)S * Np * Np + 2 * (size_t)S * 128 * Npad) * sizeof(float);     // X^T hi|lo, Lt hi|lo
 }
 
-int trtri_split_tc(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi, float* linv_lo,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int potrf_lower_batched_tc(int, int, float*, float*, int*, float*, float*, cudaStream_t, cudaEvent_t*);
+void potrf_winv_block(int, int, int, const float*, float*, cudaStream_t);
+
+// blk_done == NULL: everything on st, winv complete on entry (the two-call sequence).  Otherwise row block K starts when
+// blk_done[K] has fired on the factorisation's stream, and forms W_KK itself.
+static int trtri_tc_run(int Npad, int Np, int S, const float* L, float* winv, float* linv_hi, float* linv_lo,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st, cudaEvent_t* blk_done) {
   if (Npad <= 0 || Npad % kNpadMult) return -1;
   if (Np < Npad || Np % tc::BN) return -2;
   if (S <= 0) return -3;
@@ -901,6 +907,10 @@ int trtri_split_tc(int Npad, int Np, int S, const float* L, const float* winv, f
   const int nblk = Npad / 128;
   timing_begin("trtri_kernel", st);
   for (int K = 0; K < nblk; ++K) {
+    if (blk_done) {
+      cudaStreamWaitEvent(st, blk_done[K], 0);
+      potrf_winv_block(Npad, S, K, L, winv, st);
+    }
     trtri_diag_store_kernel<<<dim3(8, S), 256, 0, st>>>(Npad, Np, K, winv, linv_hi, linv_lo, xthi, xtlo);
     count_launch();
     if (K == 0) continue;
@@ -917,6 +927,44 @@ int trtri_split_tc(int Npad, int Np, int S, const float* L, const float* winv, f
   }
   timing_end(st);
   return check_launch("trtri_split_tc");
+}
+
+int trtri_split_tc(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi, float* linv_lo,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  return trtri_tc_run(Npad, Np, S, L, const_cast<float*>(winv), linv_hi, linv_lo, workspace, workspace_bytes, st, nullptr);
+}
+
+// Factor and invert in one call, pipelined: row block K of the inverse needs W_KK, row block K of L and the rows of the
+// inverse above it -- all final as soon as block column K of the factorisation is.  So the inversion runs ONE STEP BEHIND
+// the factorisation on a second stream instead of after it.  Both are chains of small dependent launches (32 block steps at
+// N = 4096); with few hyper-samples per GPU (the 8-GPU shape: 5) neither fills the machine and the two chains simply overlap
+// (3.5 + 3.8 ms one after the other).  With a full batch (40) each is throughput-bound and the overlap fills the bubbles
+// of the other's spine.
+int potrf_trtri_tc(int Npad, int Np, int S, float* A, float* winv, int* info, float* lhi, float* llo, float* linv_hi,
+                   float* linv_lo, void* tws, size_t tws_bytes, cudaStream_t st) {
+  if (Npad <= 0 || Npad % kNpadMult) return -1;
+  static cudaStream_t aux = nullptr;
+  static cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  static std::vector<cudaEvent_t> blk;
+  if (!aux) {
+    cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming);
+  }
+  const int nblk = Npad / 128;
+  while ((int)blk.size() < nblk) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    blk.push_back(e);
+  }
+  cudaEventRecord(ev_in, st);                      // the buffers are free / the covariance is built
+  cudaStreamWaitEvent(aux, ev_in, 0);
+  int rc = potrf_lower_batched_tc(Npad, S, A, winv, info, lhi, llo, st, blk.data());
+  if (rc) return rc;
+  rc = trtri_tc_run(Npad, Np, S, A, winv, linv_hi, linv_lo, tws, tws_bytes, aux, blk.data());
+  cudaEventRecord(ev_out, aux);
+  cudaStreamWaitEvent(st, ev_out, 0);
+  return rc;
 }
 
 // fp16 operand copy of the explicit inverse for the predict GEMM: per-sample power-of-two scale + (hi, lo) split.

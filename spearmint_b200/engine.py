@@ -84,11 +84,25 @@ class Factor(object):
         check(fn("smk_cov_build", dt)(KINDS[kind], self.N, self.N, self.D, S, ptr(X), None, ptr(hb.inv_ls),
                                       ptr(hb.amp2), ptr(hb.noise), ptr(self.L), self.Npad, st), "cov_build")
         if self.factor_impl == "tc" and dt == torch.float32 and self.Npad >= 256:
+            L = _lib.lib()
             nb = 2 * S * self.Npad * self.Npad * 4
             ws = eng.take((nb,), torch.uint8)
-            eng.give(ws)                      # scratch of this call only (stream-ordered reuse)
-            check(_lib.lib().smk_potrf_lower_batched_tc_f32(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info),
-                                                            ptr(ws), nb, st), "potrf_tc")
+            if eng.fused_inverse:
+                # factor and explicit inverse in one pipelined call (the inverse runs one block step behind on a second
+                # stream): every consumer of a tensor-core factor needs the inverse anyway
+                Np = L.smk_tc_np(self.N)
+                hi = self._take((S, Np, Np), torch.float32)
+                lo = self._take((S, Np, Np), torch.float32)
+                nt = L.smk_trtri_tc_workspace_bytes(self.Npad, Np, S)
+                wt = eng.take((nt,), torch.uint8)
+                check(L.smk_potrf_trtri_tc_f32(self.Npad, Np, S, ptr(self.L), ptr(self.winv), ptr(self.info), ptr(ws), nb,
+                                               ptr(hi), ptr(lo), ptr(wt), nt, st), "potrf_trtri_tc")
+                eng.give(ws, wt)              # scratch of this call only (the call joins back into st: stream-ordered reuse)
+                self._linv = (hi, lo, Np)
+            else:
+                eng.give(ws)                  # scratch of this call only (stream-ordered reuse)
+                check(L.smk_potrf_lower_batched_tc_f32(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info),
+                                                       ptr(ws), nb, st), "potrf_tc")
         else:
             check(fn("smk_potrf_lower_batched", dt)(self.Npad, S, ptr(self.L), ptr(self.winv), ptr(self.info), st),
                   "potrf")
@@ -250,6 +264,9 @@ class GPEIEngine(object):
         # measured: no gain (268.8 -> 272.6 ms at S=40, 37.8 -> 39.9 ms at S=5): the persistent GEMM and the generator leave no
         # SM for the side stream's kernels to run on, and two groups double the launches.  Off unless asked for.
         self.overlap = os.environ.get("SMK_FACTOR_OVERLAP", "0") == "1"
+        # tensor-core chain: factorisation and explicit inverse as one pipelined call (csrc/predict_tc.cu: potrf_trtri_tc);
+        # SMK_FUSED_INVERSE=0 runs them one after the other (the two separate entry points)
+        self.fused_inverse = os.environ.get("SMK_FUSED_INVERSE", "1") == "1"
         self._helper64 = None
 
     # ------------------------------------------------------------------ buffers
@@ -336,7 +353,7 @@ class GPEIEngine(object):
         per = self.esize * (Npad * Npad + Npad * self.NB + F * Npad + (F + 3) * ldm)
         if self.predict_impl == "tc" and self.dtype == torch.float32:
             Np = _ceil(Npad, 256)
-            per += 20 * Np * Np
+            per += 20 * Np * Np + (8 * Npad * Npad if self.fused_inverse else 0)   # + the factorisation's tf32 panel copies, live next to the inversion's workspace
             per_kxt = 4.0 * ldm * Np + 4.0 * (Np // 512 + 1) * ldm      # operand chunk + row-group-pair partials
             cap = float(21 << 30)
             s1 = budget / (per + per_kxt)
