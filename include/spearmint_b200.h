@@ -134,7 +134,12 @@ int smk_predict_f64(int kind, int N, int Npad, int M, int D, int S, const double
  *                         linv_exp: [2*S] ints (first S: exponents, rest scratch).
  *   smk_predict_tc_f32  : cross-covariance (candidate-major, fp16 hi/lo) -> D = Kxt * Linv^T on tcgen05 -> var, mu.
  * alpha: [S][Npad_alpha] (first right-hand side).  dbg_beta (tests only, may be NULL): [S][Mc][Np] dump of
- * beta^T for a single-chunk call.                                                                              */
+ * beta^T for a single-chunk call.
+ * z (may be NULL): [S][Np], z = Linv (y - mean) -- the `tmp` output of smk_linv_alpha_f32.  With z the predictive mean is
+ *   reduced in the GEMM epilogue (mu - mean = alpha . kx = z . beta) and the generator needs no alpha; then chunk 0 of the
+ *   cross-covariance can be generated AHEAD of this call, while K is still being factored:
+ *   smk_predict_tc_pregen_f32 (same workspace, same shapes; runs on an internal stream forked from `stream`), followed by
+ *   smk_predict_tc_f32(..., z, pregenerated = 1).  pregenerated = 1 without a matching pre-generation returns -21.     */
 int smk_tc_np(int N);
 size_t smk_trtri_workspace_bytes(int Np, int S);
 int smk_trtri_split_f32(int Npad, int Np, int S, const float* L, const float* winv, float* linv_hi,
@@ -188,7 +193,10 @@ int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float
                        const float* inv_ls, const float* amp2, const float* mean, const void* linv_h16,
                        const void* linv_l16, const int* linv_exp, const float* alpha, int Npad_alpha, float* mu,
                        float* var, int ldm, void* workspace, size_t workspace_bytes, float* dbg_beta, int F,
-                       const float* alpha_f, float* mu_f, void* stream);
+                       const float* alpha_f, float* mu_f, const float* z, int pregenerated, void* stream);
+int smk_predict_tc_pregen_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
+                              const float* inv_ls, const float* amp2, void* workspace, size_t workspace_bytes, int F,
+                              void* stream);
 
 /* ---- (4b) cross mean only: mu[s][f][j] = cov(X, C_j)' alpha[s][f] + mean[s]
  *          time-GP mean of EI-per-second (PSEC:442-459) and fantasy means (OPT:609).

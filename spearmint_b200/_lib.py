@@ -69,7 +69,8 @@ SIGNATURES = {
     "smk_debug_kxt_tc_timeline": ([_p, _i], _i),
     "smk_kxt_pack_f16": ([_i] * 7 + [_p] * 6 + [_i, _p, _p, _p, _i, _p, _sz, _p], _i),
     "smk_linv_pack_f16": ([_i, _i, _p, _p, _p, _p, _p, _p], _i),
-    "smk_predict_tc_f32": ([_i] * 6 + [_p] * 9 + [_i, _p, _p, _i, _p, _sz, _p, _i, _p, _p, _p], _i),
+    "smk_predict_tc_f32": ([_i] * 6 + [_p] * 9 + [_i, _p, _p, _i, _p, _sz, _p, _i, _p, _p, _p, _i, _p], _i),
+    "smk_predict_tc_pregen_f32": ([_i] * 6 + [_p] * 5 + [_sz, _i, _p], _i),
 }
 for _t in ("f32", "f64"):
     SIGNATURES.update({

@@ -89,7 +89,9 @@ int kxt_pack(int, int, int, int, int, int, int, const float*, const float*, cons
              const float*, int, __half*, __half*, float*, int, void*, size_t, cudaStream_t);
 int predict_tc(int, int, int, int, int, int, const float*, const float*, const float*, const float*, const float*,
                const __half*, const __half*, const int*, const float*, int, float*, float*, int, void*, size_t, float*,
-               int, const float*, float*, cudaStream_t);
+               int, const float*, float*, const float*, int, cudaStream_t);
+int predict_tc_pregen(int, int, int, int, int, int, const float*, const float*, const float*, const float*, void*, size_t,
+                      int, cudaStream_t);
 size_t predict_workspace_bytes_any(int, int);
 size_t potrf_ll_workspace_bytes(int, int);
 template <typename T>
@@ -263,10 +265,15 @@ int smk_predict_tc_f32(int kind, int N, int Np, int M, int D, int S, const float
                        const float* inv_ls, const float* amp2, const float* mean, const void* linv_h16,
                        const void* linv_l16, const int* linv_exp, const float* alpha, int Npad_alpha, float* mu,
                        float* var, int ldm, void* workspace, size_t workspace_bytes, float* dbg_beta, int F,
-                       const float* alpha_f, float* mu_f, void* stream) {
+                       const float* alpha_f, float* mu_f, const float* z, int pregenerated, void* stream) {
   return predict_tc(kind, N, Np, M, D, S, X, C, inv_ls, amp2, mean, reinterpret_cast<const __half*>(linv_h16),
                     reinterpret_cast<const __half*>(linv_l16), linv_exp, alpha, Npad_alpha, mu, var, ldm, workspace,
-                    workspace_bytes, dbg_beta, F, alpha_f, mu_f, ST(stream));
+                    workspace_bytes, dbg_beta, F, alpha_f, mu_f, z, pregenerated, ST(stream));
+}
+int smk_predict_tc_pregen_f32(int kind, int N, int Np, int M, int D, int S, const float* X, const float* C,
+                              const float* inv_ls, const float* amp2, void* workspace, size_t workspace_bytes, int F,
+                              void* stream) {
+  return predict_tc_pregen(kind, N, Np, M, D, S, X, C, inv_ls, amp2, workspace, workspace_bytes, F, ST(stream));
 }
 
 int smk_cross_mean_f32(int kind, int N, int Npad, int M, int D, int S, int F, const float* X, const float* C,
@@ -419,7 +426,7 @@ int smk_ei_over_hypers_host_f32(int kind, int N, int M, int D, int S, const doub
     int* lexp = reinterpret_cast<int*>(l16 + 2 * (size_t)S * Np * Np * sizeof(__half));
     if ((rc = smk_linv_pack_f16(Np, S, lhi, llo, lh16, ll16, lexp, st))) return rc;
     if ((rc = smk_predict_tc_f32(kind, N, Np, M, D, S, dX, dC, dil, da, dm, lh16, ll16, lexp, alpha, Npad, mv,
-                                 mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, st)))
+                                 mv + (size_t)S * ldm, ldm, ws, wsb, nullptr, 1, nullptr, nullptr, tmp, 0, st)))
       return rc;
   }
   if ((rc = smk_ei_sweep_f32(M, S, 1, mv, mv + (size_t)S * ldm, ldm, db, nullptr, ei, nullptr, nullptr, st))) return rc;

@@ -118,15 +118,18 @@ __device__ __forceinline__ unsigned h2_bits(__half2 h) { return *reinterpret_cas
 
 // One 32-column chunk of one accumulator row: distances -> kernel values -> scaled fp16 (hi, lo) into this lane's staging row,
 // running mean.  KIND and EDGE are compile-time: the per-pair kind switch and edge test were ~20 % of the executed instructions.
-template <int KIND, bool EDGE>
+template <int KIND, bool EDGE, bool MU>
 __device__ __forceinline__ void chunk_compute(const uint32_t (&r)[32], float2 scl2, float2 a2s, const float* al_row,
                                               unsigned char* gout_row, int nfirst, int N, float2& v) {
 #pragma unroll
   for (int k8 = 0; k8 < 4; ++k8) {             // 8 columns -> 16 bytes of hi and of lo in this lane's staging row
     unsigned ph[4], pl[4];
-    const float4 a0 = *reinterpret_cast<const float4*>(al_row + 8 * k8);
-    const float4 a1 = *reinterpret_cast<const float4*>(al_row + 8 * k8 + 4);
-    const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+    float2 ap[4];
+    if (MU) {
+      const float4 a0 = *reinterpret_cast<const float4*>(al_row + 8 * k8);
+      const float4 a1 = *reinterpret_cast<const float4*>(al_row + 8 * k8 + 4);
+      ap[0] = make_float2(a0.x, a0.y); ap[1] = make_float2(a0.z, a0.w); ap[2] = make_float2(a1.x, a1.y); ap[3] = make_float2(a1.z, a1.w);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int col = 8 * k8 + 2 * i;
@@ -139,7 +142,7 @@ __device__ __forceinline__ void chunk_compute(const uint32_t (&r)[32], float2 sc
         if (n >= N) kk.x = 0.f;
         if (n + 1 >= N) kk.y = 0.f;
       }
-      v = __ffma2_rn(kk, ap[i], v);
+      if (MU) v = __ffma2_rn(kk, ap[i], v);
       const float2 val = __fmul2_rn(kk, a2s);
       const __half2 h2 = __floats2half2_rn(val.x, val.y);
       const float2 hf = __half22float2(h2);
@@ -152,7 +155,7 @@ __device__ __forceinline__ void chunk_compute(const uint32_t (&r)[32], float2 sc
   }
 }
 
-template <int KIND>
+template <int KIND, bool MU>
 __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
   extern __shared__ unsigned char smem_raw[];
   // 1 KB alignment by OFFSET, not by integer arithmetic on the pointer: a pointer rebuilt from a uintptr_t loses its address
@@ -358,15 +361,19 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         if (f < p.S * (CW / 4)) *reinterpret_cast<float4*>(gal + (size_t)(f >> 3) * ALD + (f & 7) * 4) = apf[q];
       }
     };
-    {                                                    // first chunk of this group: tile nb = grp of the first item
+    if (MU) {                                            // first chunk of this group: tile nb = grp of the first item
       const int nb_first = grp % nblocks;
       alpha_fetch(nb_first * TN);
     }
     for (long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int crow = (int)item * p.J + j;           // candidate row inside the chunk
       const bool act = row_used && crow < p.mc_used;
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");            // the group is done with the previous item's offsets
+      // the group (MU: alpha chunk shared by its 4 warps) / the warp (rowoff rows are read by their own warp only) is done
+      // with the previous item's offsets
+      if (MU) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      else __syncwarp();
       rowoff[gt] = act ? (long long)(((size_t)s * p.Mc + crow) * p.Np) : -1;
+      if (!MU) __syncwarp();
       float2 v = make_float2(0.f, 0.f);
       for (int nb = 0; nb < nblocks; ++nb, ++t) {
         if ((int)(t % NGRP) != grp) continue;
@@ -383,15 +390,17 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         for (int cq = 0; cq < TN; cq += CW) {
           uint32_t r[32];
           tmem_ld32(t0 + cq, r);
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // previous chunk's readers are done
-          alpha_store();                                                         // this chunk's alpha: fetched a chunk ago
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // (also publishes rowoff of a new item)
-          // next chunk of this group: same tile, or the group's next tile (t + NGRP; alpha does not depend on the item)
-          alpha_fetch((cq + CW < TN) ? n0 + cq + CW : (int)(((t + NGRP) % nblocks) * TN));
+          if (MU) {
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");        // previous chunk's readers are done
+            alpha_store();                                                       // this chunk's alpha: fetched a chunk ago
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");        // (also publishes rowoff of a new item)
+            // next chunk of this group: same tile, or the group's next tile (t + NGRP; alpha does not depend on the item)
+            alpha_fetch((cq + CW < TN) ? n0 + cq + CW : (int)(((t + NGRP) % nblocks) * TN));
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (act) {
-            if (edge) chunk_compute<KIND, true>(r, scl2, a2s, al_row, gout + lane * OLD, n0 + cq, p.N, v);
-            else chunk_compute<KIND, false>(r, scl2, a2s, al_row, gout + lane * OLD, n0 + cq, p.N, v);
+            if (edge) chunk_compute<KIND, true, MU>(r, scl2, a2s, al_row, gout + lane * OLD, n0 + cq, p.N, v);
+            else chunk_compute<KIND, false, MU>(r, scl2, a2s, al_row, gout + lane * OLD, n0 + cq, p.N, v);
           }
           __syncwarp();
           // coalesced write-out: each store instruction covers 4 rows x (64 B hi, 64 B lo); lane -> (row, half, 16-byte piece)
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         if (lane == 0) mbar_arrive(&t_empty[b]);
         if (stamp) p.tl[t * 8 + 7] = clock64();
       }
-      if (act) p.mu_partial[((size_t)grp * p.S + s) * p.Mc + crow] = v.x + v.y;
+      if (MU && act) p.mu_partial[((size_t)grp * p.S + s) * p.Mc + crow] = v.x + v.y;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -523,15 +532,27 @@ int kxt_tc(void* ws, int kind, int N, int Np, int M, int c_begin, int Mc, int mc
   const int grid = (int)std::min<long>(a.nitems, num_sms());
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(ktc::kxt_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(ktc::kxt_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(ktc::kxt_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(ktc::kxt_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  switch (kind) {
-    case 0: case 1: ktc::kxt_tc_kernel<1><<<grid, ktc::THREADS, smem, st>>>(a); break;
-    case 2: ktc::kxt_tc_kernel<2><<<grid, ktc::THREADS, smem, st>>>(a); break;
-    default: ktc::kxt_tc_kernel<3><<<grid, ktc::THREADS, smem, st>>>(a); break;
+  // alpha == NULL: covariance operand only (no predictive-mean partials; predict_tc reduces the mean in its GEMM epilogue)
+  if (alpha) {
+    switch (kind) {
+      case 0: case 1: ktc::kxt_tc_kernel<1, true><<<grid, ktc::THREADS, smem, st>>>(a); break;
+      case 2: ktc::kxt_tc_kernel<2, true><<<grid, ktc::THREADS, smem, st>>>(a); break;
+      default: ktc::kxt_tc_kernel<3, true><<<grid, ktc::THREADS, smem, st>>>(a); break;
+    }
+  } else {
+    switch (kind) {
+      case 0: case 1: ktc::kxt_tc_kernel<1, false><<<grid, ktc::THREADS, smem, st>>>(a); break;
+      case 2: ktc::kxt_tc_kernel<2, false><<<grid, ktc::THREADS, smem, st>>>(a); break;
+      default: ktc::kxt_tc_kernel<3, false><<<grid, ktc::THREADS, smem, st>>>(a); break;
+    }
   }
   count_launch();
   return check_launch("kxt_tc");

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
   const float* ils = inv_ls + (long)s * D;
   const float a2 = amp2[s];
   const float2 a2s = dup2(a2 * ldexpf(1.f, kx_exp(a2)));     // amp2 * 2^ea: largest entry lands in [2^14, 2^15)
-  const float* al = alpha + (long)s * Npad_alpha;
+  const float* al = alpha ? alpha + (long)s * Npad_alpha : nullptr;   // NULL: no mean here (predict_tc forms it from beta)
   float2 mdot[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) mdot[r] = make_float2(0.f, 0.f);
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int n = n0 + (c >> 1) * 64 + tx * 4 + (c & 1) * 2;
-      av[c] = make_float2((n < N) ? al[n] : 0.f, (n + 1 < N) ? al[n + 1] : 0.f);
+      av[c] = al ? make_float2((n < N) ? al[n] : 0.f, (n + 1 < N) ? al[n + 1] : 0.f) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(256, 2) kxt_kernel(int kind, int N, int Np, in
     }
   }
   // mean: reduce the per-thread row partials over the 16 column-threads (fixed order -> deterministic)
+  if (!al) return;
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 8; ++r) red[tx][tile_row(ty, r)] = mdot[r].x + mdot[r].y;
@@ -418,6 +419,8 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 struct Args {
   int S, Np, Mc, ntiles, npairs, ngroups, ldp;   // Mc = candidates per chunk (multiple of 128); ldp = partial stride
   float* partial;                                 // [npairs][S][ldp]
+  const float* z;                                 // optional [S][Np]: z = Linv (y - mean); then mu = mean + z . beta is reduced here
+  float* mpartial;                                // [npairs][S][ldp] partial sums of z . beta
   float* dbg;                                     // optional [S][Mc][Np] dump of beta^T (tests only)
   // rectangular mode (fantasy means, OPT:609): B = alpha^T [S][ngroups*256][Np], full k range, one group per item,
   // the epilogue stores  D[c][f] + mean[s]  to mu_f[s][f][c_begin + c]  instead of reducing squares
@@ -587,7 +590,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
     const int row = q * 32 + lane;
     uint32_t buf = 0, bphase = 0;
     for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
-      float acc = 0.f;
+      float acc = 0.f, accm = 0.f;
       Item it0 = get_item(p, w, 0);
       for (int h = 0; h < 2; ++h) {
         const Item it = get_item(p, w, h);
@@ -603,10 +606,22 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           tmem_ld32(t0 + c0, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (p.mode == 0) {
+            if (p.z) {                          // predictive mean from the same accumulator: mu - mean = alpha . kx = z . beta
+              const float4* zq = reinterpret_cast<const float4*>(p.z + (long)it.s * p.Np + it.g * BN + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]) * scl;
-              acc = fmaf(v, v, acc);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 z4 = __ldg(zq + (j >> 2));     // same address in every lane: broadcast
+                const float v0 = __uint_as_float(r[j]) * scl, v1 = __uint_as_float(r[j + 1]) * scl;
+                const float v2 = __uint_as_float(r[j + 2]) * scl, v3 = __uint_as_float(r[j + 3]) * scl;
+                acc = fmaf(v0, v0, acc); acc = fmaf(v1, v1, acc); acc = fmaf(v2, v2, acc); acc = fmaf(v3, v3, acc);
+                accm = fmaf(v0, z4.x, accm); accm = fmaf(v1, z4.y, accm); accm = fmaf(v2, z4.z, accm); accm = fmaf(v3, z4.w, accm);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float v = __uint_as_float(r[j]) * scl;
+                acc = fmaf(v, v, acc);
+              }
             }
             if (p.dbg) {
               float* o = p.dbg + ((long)it.s * p.Mc + it.tile * BM + row) * p.Np + it.g * BN + c0;
@@ -665,7 +680,10 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         buf ^= 1;
         if (buf == 0) bphase ^= 1;
       }
-      if (p.mode == 0) p.partial[((long)it0.pr * p.S + it0.s) * p.ldp + it0.tile * BM + row] = acc;
+      if (p.mode == 0) {
+        p.partial[((long)it0.pr * p.S + it0.s) * p.ldp + it0.tile * BM + row] = acc;
+        if (p.z) p.mpartial[((long)it0.pr * p.S + it0.s) * p.ldp + it0.tile * BM + row] = accm;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -679,12 +697,18 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
 __global__ void finish_var_kernel(int M, int c_begin, int Mc, int S, int npairs, int ldp, const float* __restrict__ partial,
                                   const float* __restrict__ amp2, float* __restrict__ var, int ldm, int nmp,
                                   const float* __restrict__ mu_partial, const float* __restrict__ mean,
-                                  float* __restrict__ mu) {
+                                  float* __restrict__ mu, const float* __restrict__ mpartial) {
   int c = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
   if (c >= Mc || c_begin + c >= M) return;
   float t = 0.f;
   for (int pr = 0; pr < npairs; ++pr) t += partial[((long)pr * S + s) * ldp + c];
   var[(long)s * ldm + c_begin + c] = amp2[s] * 1.000001f - t;
+  if (mpartial) {                               // mean reduced by the GEMM epilogue: mu = mean + z . beta
+    float m = 0.f;
+    for (int pr = 0; pr < npairs; ++pr) m += mpartial[((long)pr * S + s) * ldp + c];
+    mu[(long)s * ldm + c_begin + c] = mean[s] + m;
+    return;
+  }
   if (nmp > 0) {
     float m = 0.f;
     for (int j = 0; j < nmp; ++j) m += mu_partial[((long)j * S + s) * ldp + c];
@@ -1038,7 +1062,7 @@ static int fant_rows(int F) { return F > 1 ? ((F + tc::BN - 1) / tc::BN) * tc::B
 size_t predict_tc_workspace_bytes(int Np, int M, int S, int F) {
   size_t mc = tc_chunk_cands(Np, M, S, kTcBudget);
   int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2, nbuf = tc_nbuf(Np, M, S, kTcBudget);
-  return (size_t)nbuf * S * mc * Np * 2 * sizeof(__half) + (size_t)npairs * S * mc * sizeof(float) +
+  return (size_t)nbuf * S * mc * Np * 2 * sizeof(__half) + 2 * (size_t)npairs * S * mc * sizeof(float) +
          2 * (size_t)S * fant_rows(F) * Np * sizeof(__half) + (size_t)S * sizeof(int) + 1024 +
          kxt_tc_workspace_bytes(Np, (int)mc, S, M, kKxtWsD);
 }
@@ -1076,10 +1100,71 @@ int kxt_pack(int impl, int kind, int N, int Np, int M, int D, int S, const float
   return check_launch("kxt_pack");
 }
 
+// Chunk 0 of the cross-covariance generated AHEAD of the GEMM, on an internal stream forked from `st`: the generator needs
+// the observations, the candidates and the kernel hyper-parameters only (the mean comes out of the GEMM epilogue as z . beta),
+// so it runs while the caller's stream factors and inverts K.  predict_tc(..., pregenerated = 1) with the same workspace
+// picks the chunk up.  One outstanding pre-generation per process.
+struct PregenState {
+  bool valid = false;
+  void* ws = nullptr;
+  int M = 0, S = 0, Np = 0, N = 0;
+  cudaEvent_t done = nullptr, fork = nullptr;
+  cudaStream_t stream = nullptr;
+};
+static PregenState g_pregen;
+
+int predict_tc_pregen(int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
+                      const float* amp2, void* workspace, size_t workspace_bytes, int F, cudaStream_t st) {
+  if (kind < 0 || kind > 3) return -1;
+  if (N <= 0 || Np < N || Np % tc::BN) return -3;
+  if (M <= 0 || D <= 0 || S <= 0) return -4;
+  if (!X || !Cc || !inv_ls || !amp2) return -7;
+  const bool fant = F > 1;
+  if (!workspace || workspace_bytes < predict_tc_workspace_bytes(Np, M, S, fant ? F : 1)) return -20;
+  if (tc_nbuf(Np, M, S, kTcBudget) != 1) return -22;
+  const int Mc = (int)tc_chunk_cands(Np, M, S, kTcBudget);
+  const int ngroups = Np / tc::BN, npairs = (ngroups + 1) / 2;
+  const size_t kelems = (size_t)S * Mc * Np;
+  __half* kbase = reinterpret_cast<__half*>(workspace);
+  float* partial = reinterpret_cast<float*>(kbase + 2 * kelems);
+  const int Fp = fant ? fant_rows(F) : 0;
+  __half* ahi = reinterpret_cast<__half*>(partial + 2 * (size_t)npairs * S * Mc);
+  int* fexp = reinterpret_cast<int*>(ahi + 2 * (size_t)S * Fp * Np);
+  void* kws = reinterpret_cast<void*>(fexp + S);
+  static int gen_env = -1;
+  if (gen_env < 0) { const char* e = getenv("SMK_KXT_IMPL"); gen_env = (e && !strcmp(e, "simt")) ? 0 : 1; }
+  const bool gen_tc = gen_env == 1 && kxt_tc_preferred(D, S);
+  PregenState& g = g_pregen;
+  if (!g.stream) {
+    cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming);
+  }
+  cudaEventRecord(g.fork, st);                       // inputs uploaded, the workspace's previous users done
+  cudaStreamWaitEvent(g.stream, g.fork, 0);
+  const int mc_used = min(Mc, (M + 127) / 128 * 128);
+  timing_begin("kxt_kernel", g.stream);
+  if (gen_tc) {
+    int rc = kxt_tc_prepare(kws, N, Np, M, Mc, D, S, X, Cc, g.stream);
+    if (rc) return rc;
+    rc = kxt_tc(kws, kind, N, Np, M, 0, Mc, mc_used, D, S, inv_ls, amp2, nullptr, 0, kbase, kbase + kelems, g.stream);
+    if (rc) return rc;
+  } else {
+    kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, g.stream>>>(kind, N, Np, M, 0, Mc, D, X, Cc, inv_ls, amp2, nullptr, nullptr, 0,
+                                                             kbase, kbase + kelems, nullptr, 0);
+    count_launch();
+  }
+  timing_end(g.stream);
+  cudaEventRecord(g.done, g.stream);
+  g.valid = true; g.ws = workspace; g.M = M; g.S = S; g.Np = Np; g.N = N;
+  return check_launch("predict_tc_pregen");
+}
+
 int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, const float* Cc, const float* inv_ls,
                const float* amp2, const float* mean, const __half* linv_hi, const __half* linv_lo, const int* linv_exp,
                const float* alpha, int Npad_alpha, float* mu, float* var, int ldm, void* workspace,
-               size_t workspace_bytes, float* dbg, int F, const float* alpha_f, float* mu_f, cudaStream_t st) {
+               size_t workspace_bytes, float* dbg, int F, const float* alpha_f, float* mu_f, const float* z,
+               int pregenerated, cudaStream_t st) {
   if (kind < 0 || kind > 3) return -1;
   if (N <= 0) return -2;
   if (Np < N || Np % tc::BN) return -3;
@@ -1096,8 +1181,9 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   const size_t kelems = (size_t)S * Mc * Np;                               // one Kxt buffer, elements per half-array
   __half* kbase = reinterpret_cast<__half*>(workspace);                    // [nbuf]{hi [S][Mc][Np] | lo [S][Mc][Np]}
   float* partial = reinterpret_cast<float*>(kbase + (size_t)nbuf * 2 * kelems);
+  float* mpartial = partial + (size_t)npairs * S * Mc;                           // z . beta partial sums (when z is given)
   const int Fp = fant ? fant_rows(F) : 0;
-  __half* ahi = reinterpret_cast<__half*>(partial + (size_t)npairs * S * Mc);   // alpha^T hi | lo  [S][Fp][Np]
+  __half* ahi = reinterpret_cast<__half*>(mpartial + (size_t)npairs * S * Mc);  // alpha^T hi | lo  [S][Fp][Np]
   __half* alo = ahi + (size_t)S * Fp * Np;
   int* fexp = reinterpret_cast<int*>(alo + (size_t)S * Fp * Np);
   // generator: the tensor-core kernel of kxt_tc.cu (contraction over dimensions on tcgen05) wherever it applies (D <= 32,
@@ -1106,10 +1192,19 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
   static int gen_env = -1;
   if (gen_env < 0) { const char* e = getenv("SMK_KXT_IMPL"); gen_env = (e && !strcmp(e, "simt")) ? 0 : 1; }
   const bool gen_tc = gen_env == 1 && kxt_tc_preferred(D, S) && nbuf == 1;
-  const int nmp = gen_tc ? kxt_tc_ngroups(Np) : 0;
+  const int nmp = (gen_tc && !z) ? kxt_tc_ngroups(Np) : 0;
   void* kws = reinterpret_cast<void*>(fexp + S);
   float* mu_partial = gen_tc ? kxt_tc_mu_partial(kws, Np, Mc, S, M, D) : nullptr;
-  if (gen_tc) {
+  const float* gen_alpha = z ? nullptr : alpha;     // with z the mean comes out of the GEMM epilogue: the generator needs no alpha
+  // chunk 0 may have been generated ahead of time (predict_tc_pregen: while the factorisation was running)
+  const bool pre = pregenerated && z && nbuf == 1 && g_pregen.valid && g_pregen.ws == workspace && g_pregen.M == M &&
+                   g_pregen.S == S && g_pregen.Np == Np && g_pregen.N == N;
+  if (pregenerated && !pre) return -21;
+  if (g_pregen.valid && g_pregen.ws == workspace) {   // picked up below -- or abandoned by the caller: either way ordered behind it
+    cudaStreamWaitEvent(st, g_pregen.done, 0);
+    g_pregen.valid = false;
+  }
+  if (!pre && gen_tc) {
     int rc = kxt_tc_prepare(kws, N, Np, M, Mc, D, S, X, Cc, st);
     if (rc) return rc;
   }
@@ -1162,15 +1257,17 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     __half* kh = kbase + (size_t)b * 2 * kelems;
     const int mc_used = min(Mc, ((M - c_begin) + 127) / 128 * 128);
     if (overlap && ci >= 2) cudaStreamWaitEvent(aux, ev_mma[b], 0);      // buffer b is free again
-    timing_begin("kxt_kernel", kst);
-    if (gen_tc) {
-      int rc = kxt_tc(kws, kind, N, Np, M, c_begin, Mc, mc_used, D, S, inv_ls, amp2, alpha, Npad_alpha, kh, kh + kelems, kst);
-      if (rc) return rc;
-    } else {
-      kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, kst>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
-                                                          alpha, Npad_alpha, kh, kh + kelems, mu, ldm);
+    if (!(pre && ci == 0)) {
+      timing_begin("kxt_kernel", kst);
+      if (gen_tc) {
+        int rc = kxt_tc(kws, kind, N, Np, M, c_begin, Mc, mc_used, D, S, inv_ls, amp2, gen_alpha, Npad_alpha, kh, kh + kelems, kst);
+        if (rc) return rc;
+      } else {
+        kxt_kernel<<<dim3(mc_used / 128, S), 256, 0, kst>>>(kind, N, Np, M, c_begin, Mc, D, X, Cc, inv_ls, amp2, mean,
+                                                            gen_alpha, Npad_alpha, kh, kh + kelems, mu, ldm);
+      }
+      timing_end(kst);
     }
-    timing_end(kst);
     if (overlap) {
       cudaEventRecord(ev_kxt[b], aux);
       cudaStreamWaitEvent(st, ev_kxt[b], 0);
@@ -1178,7 +1275,7 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     tc::Args a;
     tc_args_init(a);
     a.S = S; a.Np = Np; a.Mc = Mc; a.ntiles = mc_used / tc::BM; a.npairs = npairs; a.ngroups = ngroups; a.ldp = Mc;
-    a.partial = partial; a.dbg = dbg;
+    a.partial = partial; a.dbg = dbg; a.z = z; a.mpartial = mpartial;
     a.M = M; a.c_begin = c_begin; a.ldm = ldm; a.mean = mean;
     a.mode = 0; a.f16 = 1; a.amp2 = amp2; a.bexp = linv_exp;
     { const char* e = getenv("SMK_TC_A_EVICT_FIRST"); a.a_evict_first = (e && e[0] == '1') ? 1 : 0; }
@@ -1188,11 +1285,12 @@ int predict_tc(int kind, int N, int Np, int M, int D, int S, const float* X, con
     tc::predict_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mAhi[b], mAlo[b], mBhi, mBlo, a);
     timing_end(st);
     tc::finish_var_kernel<<<dim3((mc_used + 255) / 256, S), 256, 0, st>>>(M, c_begin, mc_used, S, npairs, Mc, partial,
-                                                                        amp2, var, ldm, nmp, mu_partial, mean, mu);
+                                                                        amp2, var, ldm, nmp, mu_partial, mean, mu,
+                                                                        z ? mpartial : nullptr);
     count_launch(3);
     if (fant) {      // fantasy means: same Kxt chunk against alpha^T, rectangular k range (OPT:609)
       tc::Args r = a;
-      r.mode = 1; r.F = F; r.mu_f = mu_f; r.bexp = fexp; r.ngroups = Fp / tc::BN; r.npairs = r.ngroups;
+      r.mode = 1; r.F = F; r.mu_f = mu_f; r.bexp = fexp; r.z = nullptr; r.ngroups = Fp / tc::BN; r.npairs = r.ngroups;
       long nit = (long)S * r.ntiles * r.npairs;
       int gr = (int)std::min<long>(nit, num_sms());
       timing_begin("predict_tc_kernel_rect", st);

@@ -165,6 +165,7 @@ class Factor(object):
         tmp = torch.empty((S, Np), dtype=torch.float32, device=eng.device)
         check(L.smk_linv_alpha_f32(self.N, Np, S, ptr(hi), ptr(lo), ptr(y), ptr(self.hb.mean), ptr(alpha), self.Npad,
                                    ptr(tmp), eng.stream()), "linv_alpha")
+        self._z = tmp          # z = Linv (y - mean): the predict GEMM reduces the mean from it (mu - mean = z . beta)
         return alpha
 
     def guard(self, rows):
@@ -267,6 +268,14 @@ class GPEIEngine(object):
         # tensor-core chain: factorisation and explicit inverse as one pipelined call (csrc/predict_tc.cu: potrf_trtri_tc);
         # SMK_FUSED_INVERSE=0 runs them one after the other (the two separate entry points)
         self.fused_inverse = os.environ.get("SMK_FUSED_INVERSE", "1") == "1"
+        # Opt-in (SMK_MEAN_FROM_GEMM=1, SMK_PREGEN=1): predictive mean reduced in the GEMM epilogue (mu - mean = z . beta,
+        # z = Linv (y - mean)) instead of in the generator (alpha . kx) -- the generator then depends on nothing the
+        # factorisation produces, and the first candidate chunk is generated on a second stream WHILE K is factored and
+        # inverted.  Measured (profiles/r02_pregen_experiment.md): 2 % at 40 hyper-samples, nothing at 5 (the generator
+        # starves the factorisation's small kernels), and the mean inherits the tensor-core accumulation error of beta
+        # (headline 6.9e-4 -> 1.3e-3 of max EI, C5 1.3e-3 -> 3.3e-3): accuracy first, so both stay off.
+        self.mean_from_gemm = os.environ.get("SMK_MEAN_FROM_GEMM", "0") == "1"
+        self.pregen_enabled = self.mean_from_gemm and os.environ.get("SMK_PREGEN", "0") == "1"
         self._helper64 = None
 
     # ------------------------------------------------------------------ buffers
@@ -391,9 +400,29 @@ class GPEIEngine(object):
                                           ptr(hb.amp2), None, ptr(out), M, self.stream()), "cov_build")
         return out
 
-    def predict(self, kind, fac, C_dev, alpha, impl=None, dbg_beta=None, alpha_f=None, F=1):
+    def pregen(self, kind, X_dev, C_dev, hb, F=1):
+        """Queues the cross-covariance operand of the first candidate chunk on the library's generator stream (forked from
+        ours) and returns C_dev as the token ei_prepared() hands back to predict(); None if this shape is not pre-generated
+        (two-buffer chunking)."""
+        L = _lib.lib()
+        N, D = X_dev.shape
+        M = C_dev.shape[0]
+        Np = L.smk_tc_np(N)
+        nb = L.smk_predict_tc_workspace_bytes(Np, M, hb.S, F)
+        if self._ws_tc is None or self._ws_tc.numel() < nb:
+            self._ws_tc = None
+            self._ws_tc = torch.empty((nb,), dtype=torch.uint8, device=self.device)
+        rc = L.smk_predict_tc_pregen_f32(KINDS[kind], N, Np, M, D, hb.S, ptr(X_dev), ptr(C_dev), ptr(hb.inv_ls), ptr(hb.amp2),
+                                         ptr(self._ws_tc), self._ws_tc.numel(), F, self.stream())
+        if rc == -22:
+            return None
+        check(rc, "predict_tc_pregen")
+        return C_dev
+
+    def predict(self, kind, fac, C_dev, alpha, impl=None, dbg_beta=None, alpha_f=None, F=1, pregenerated=False):
         """Predictive mean / variance at the candidates for every sample of the factor batch.  With ``alpha_f``
-        ([S][F][Npad], tensor-core path) also the F fantasy means, returned as a third tensor [S][F][ldm]."""
+        ([S][F][Npad], tensor-core path) also the F fantasy means, returned as a third tensor [S][F][ldm].
+        ``pregenerated``: the first candidate chunk's cross-covariance was queued by pregen() for exactly these inputs."""
         hb, dt = fac.hb, self.dtype
         M = C_dev.shape[0]
         ldm = _ceil(M, 128)
@@ -407,10 +436,12 @@ class GPEIEngine(object):
                 self._ws_tc = None
                 self._ws_tc = torch.empty((nb,), dtype=torch.uint8, device=self.device)
             mu_f = torch.empty((hb.S, F, ldm), dtype=dt, device=self.device) if alpha_f is not None else None
+            z = getattr(fac, "_z", None) if self.mean_from_gemm else None
             check(L.smk_predict_tc_f32(KINDS[kind], fac.N, Np, M, fac.D, hb.S, ptr(fac.X), ptr(C_dev), ptr(hb.inv_ls),
                                        ptr(hb.amp2), ptr(hb.mean), ptr(h16), ptr(l16), ptr(lexp), ptr(alpha), fac.Npad,
                                        ptr(mu), ptr(var), ldm, ptr(self._ws_tc), nb, ptr(dbg_beta),
-                                       F if alpha_f is not None else 1, ptr(alpha_f), ptr(mu_f), self.stream()),
+                                       F if alpha_f is not None else 1, ptr(alpha_f), ptr(mu_f), ptr(z),
+                                       1 if (pregenerated and z is not None) else 0, self.stream()),
                   "predict_tc")
             if alpha_f is not None:
                 return mu, var, ldm, mu_f
@@ -475,10 +506,12 @@ class GPEIEngine(object):
 
     # ------------------------------------------------------------------ candidate-independent state
     def prepare(self, kind, hyper_samples, comp, pend, vals, normals=None, time_hyper_samples=None, durs_log=None,
-                resident=None):
+                resident=None, cand_dev=None):
         """Factor + alpha (+ fantasies, + time GP) for one chunk of hyper-samples.  ``resident`` = dict(X, y, best,
-        hb) of tensors already in HBM (the bench's `value` leg)."""
+        hb) of tensors already in HBM (the bench's `value` leg).  ``cand_dev``: the candidates the first sweep will be
+        over, if known -- their cross-covariance is then generated while the factorisation runs."""
         p = Prepared()
+        p.pregen = None
         p.kind = kind
         p.host = dict(hyper_samples=hyper_samples, comp=comp, pend=pend, vals=vals, normals=normals,
                       time_hyper_samples=time_hyper_samples, durs_log=durs_log)
@@ -500,6 +533,9 @@ class GPEIEngine(object):
         if P == 0:
             t = self._t0()
             chain = self.chain_for(Xo.shape[0])
+            if (cand_dev is not None and chain == "tc" and self.factor_impl == "tc" and self.pregen_enabled
+                    and self.guard_threshold <= 0):
+                p.pregen = self.pregen(kind, Xo, cand_dev, hb)
             fac = self.factor(kind, Xo, hb, factor_impl=chain if self.factor_impl == "tc" else "simt")
             self._t1("cov_potrf", t)
             t = self._t0()
@@ -606,7 +642,10 @@ class GPEIEngine(object):
         if p.P > 0 and impl == "tc" and p.F > 1:
             _, var, _, mu = self.predict(kind, fac, Cd, p.pred_alpha, impl=impl, alpha_f=p.alpha, F=p.F)   # OPT:605-610
         else:
-            mu, var, _ = self.predict(kind, fac, Cd, p.pred_alpha, impl=impl)      # OPT:544-548 / 605-610
+            pre = getattr(p, "pregen", None)
+            p.pregen = None
+            pre = pre is not None and pre.data_ptr() == Cd.data_ptr() and impl == "tc"
+            mu, var, _ = self.predict(kind, fac, Cd, p.pred_alpha, impl=impl, pregenerated=pre)   # OPT:544-548 / 605-610
             if p.P > 0:
                 mu = self.cross_mean(kind, fac, Cd, p.alpha, p.F)                  # OPT:609
             else:
@@ -688,7 +727,7 @@ class GPEIEngine(object):
             nrm = normals[s0:s0 + chunk] if (normals is not None and np.ndim(normals) == 3) else normals
             prep = self.prepare(kind, hyper_samples[s0:s0 + chunk], comp, pend, vals, nrm,
                                 None if time_hyper_samples is None else time_hyper_samples[s0:s0 + chunk],
-                                durs_log, resident=r)
+                                durs_log, resident=r, cand_dev=Cd)
             ei, _ = self.ei_prepared(prep, Cd, want_matrix, ei_sum, cand_host=cand)
             prep.fac.check_pd()     # one host sync per chunk, after everything is queued
             if want_matrix:

@@ -96,3 +96,28 @@ def test_c4_per_second(eng):
     ref = np.stack([O.compute_ei_per_s(bench.KIND, h, th, comp, pend, cand, vals, durs) for h, th in zip(hs, ths)], axis=1)
     ei = eng.ei_over_hypers(bench.KIND, hs, comp, pend, cand, vals, None, ths, durs)
     _assert_parity(ei, ref)
+
+
+def test_mean_from_gemm_and_pregeneration_opt_in(eng):
+    """The opt-in variant of the tensor-core chain (engine.mean_from_gemm / pregen_enabled: mean reduced in the GEMM
+    epilogue as z . beta, first candidate chunk generated while K is factored) keeps the stated tolerance and is
+    actually taken: a pre-generated chunk is consumed by the sweep."""
+    comp, cand, vals, hs = _subset("c3", 2, 4096)
+    pend = np.zeros((0, comp.shape[1]))
+    ref = O.ei_over_hypers(bench.KIND, hs, comp, pend, cand, vals)
+    base = eng.ei_over_hypers(bench.KIND, hs, comp, pend, cand, vals)
+    saved = (eng.mean_from_gemm, eng.pregen_enabled)
+    eng.mean_from_gemm, eng.pregen_enabled = True, True
+    try:
+        Cd = eng.to_dev(cand)
+        prep = eng.prepare(bench.KIND, hs, comp, None, vals, cand_dev=Cd)
+        assert prep.pregen is not None                        # queued next to the factorisation
+        ei_d, _ = eng.ei_prepared(prep, Cd, True, None, cand_host=cand)
+        assert prep.pregen is None                            # ... and consumed
+        ei = ei_d[:, :cand.shape[0]].double().cpu().numpy().T
+        again = eng.ei_over_hypers(bench.KIND, hs, comp, pend, cand, vals)
+    finally:
+        eng.mean_from_gemm, eng.pregen_enabled = saved
+    _assert_parity(ei, ref)
+    np.testing.assert_array_equal(again, ei)                  # same result through the public call
+    assert np.abs(ei - base).max() <= 2 * TOL * ref.max()     # and close to the default path
