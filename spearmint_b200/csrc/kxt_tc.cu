@@ -29,10 +29,10 @@
 // the default; predict_tc() uses the SIMT generator otherwise, and always for D > 32 or when the shared-memory budget of
 // this kernel does not fit the sample count.
 //
-// Roles in a CTA of 16 warps:  warps 0-3 producers (thread = observation row: q for the J candidate slots -> fp16 (hi, lo)
-// -> shared memory in the 64-byte-swizzled K-major layout, one [128 x 64 B] block per candidate slot; lane 0 of warp 3 also
-// issues the tile's MMAs; warp 3 owns the TMEM allocation);  warps 4-15 three epilogue
-// groups (tile t -> group t mod 3), 4 TMEM buffers of 128 columns.  Work item = J candidates x all observations.
+// Roles in a CTA of 17 warps:  warps 0-3 producers (thread = observation row: q for the J candidate slots -> fp16 (hi, lo)
+// -> shared memory in the 64-byte-swizzled K-major layout, one [128 x 64 B] block per candidate slot; warp 3 owns the TMEM
+// allocation);  warps 4-15 three epilogue groups (tile t -> group t mod 3), 4 TMEM buffers of 128 columns;  warp 16: lane 0
+// issues the MMAs of every tile.  Work item = J candidates x all observations.
 #include <cuda_fp16.h>
 #include <cuda.h>
 
@@ -57,7 +57,7 @@ constexpr int NGRP = 3;            // epilogue groups
 constexpr int MAXD = 32;           // padded dimension limit
 constexpr int MAXK = 96;           // J * Dp limit: one q stage = 128 x 96 halves x (hi, lo) = 48 KB
 constexpr int MAXS = 64;           // samples per launch (one sample per TMEM lane: <= 128; the alpha prefetch holds MAXS / 16 float4 per thread)
-constexpr int THREADS = 16 * 32;
+constexpr int THREADS = 17 * 32;     // 4 producer warps, 12 epilogue warps, 1 MMA-issue warp
 constexpr int CW = 32;             // columns per epilogue chunk (one tcgen05.ld.x32)
 constexpr int ALD = CW + 4;        // row length (floats) of the staged alpha chunk: 144-byte stride -> conflict-free row reads
 constexpr int OLD = 144;           // bytes per row of the output staging: 64 B hi | 64 B lo | 16 B pad (conflict-free both ways)
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
 #pragma unroll
         for (int d = 0; d < MAXD; ++d) xn[d] = __ldg(p.Xp + (size_t)d * p.Np + nbn * TN + r);
         const int st = (int)(t % BSTAGES);
-        mbar_wait_relaxed(&b_empty[st], (uint32_t)(((t / BSTAGES) & 1) ^ 1));
+        mbar_wait_relaxed(&b_empty[st], (uint32_t)(((t / BSTAGES) & 1) ^ 1), 128);
         const bool stamp = p.tl && blockIdx.x == 0 && t < TL_TILES;
         if (stamp && tid == 0) p.tl[t * 8 + 0] = clock64();
         unsigned char* bh = sB + (size_t)st * 2 * BH;
@@ -288,15 +288,32 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&b_full[st]);
         if (stamp && tid == 0) p.tl[t * 8 + 1] = clock64();
-        if (warp == 3 && lane == 0) {                  // MMA issue for this tile
-          const int b = (int)(t % TBUF);
+        __syncwarp();
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) xc[d] = xn[d];
+      }
+    }
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------------------------------------ MMA issue
+    // Its own warp: when lane 0 of a producer warp issued the MMAs, that warp could not start the next tile before the
+    // other three had delivered this one and a TMEM buffer was free -- the slowest producer set the pace, and its
+    // single-lane spin (4.8e8 loop iterations per launch, a quarter of all executed instructions in the r02 profile) sat
+    // in the producers' own issue slots.
+    if (lane == 0) {
+      const uint64_t whi = desc_sw64(smem_u32(sW)), wlo = desc_sw64(smem_u32(sW + WH));
+      const int ksteps = K / 16;
+      long t = 0;
+      for (long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        for (int nb = 0; nb < nblocks; ++nb, ++t) {
+          const int st = (int)(t % BSTAGES), b = (int)(t % TBUF);
+          const bool stamp = p.tl && blockIdx.x == 0 && t < TL_TILES;
           if (stamp) p.tl[t * 8 + 2] = clock64();
-          mbar_wait(&t_empty[b], (uint32_t)(((t / TBUF) & 1) ^ 1));
-          mbar_wait(&b_full[st], (uint32_t)((t / BSTAGES) & 1));
+          mbar_wait_relaxed(&t_empty[b], (uint32_t)(((t / TBUF) & 1) ^ 1), 32);
+          mbar_wait_relaxed(&b_full[st], (uint32_t)((t / BSTAGES) & 1), 32);
           if (stamp) p.tl[t * 8 + 3] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d = tmem_base + (uint32_t)b * TN;
-          const uint32_t sb = smem_u32(bh);
+          const uint32_t sb = smem_u32(sB + (size_t)st * 2 * BH);
           const uint64_t bhi = desc_sw64(sb), blo = desc_sw64(sb + BH);
           for (int q = 0; q < ksteps; ++q) {
             const uint64_t ko = (uint64_t)(((q >> 1) * SLOT_BYTES + (q & 1) * 32) >> 4);   // slot block, then 32 B inside the row
@@ -308,9 +325,6 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
           umma_commit(&t_full[b]);
           if (stamp) p.tl[t * 8 + 4] = clock64();
         }
-        __syncwarp();
-#pragma unroll
-        for (int d = 0; d < MAXD; ++d) xc[d] = xn[d];
       }
     }
   } else {
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) kxt_tc_kernel(Args p) {
         const bool edge = n0 + TN > p.N;
         const bool stamp = p.tl && blockIdx.x == 0 && t < TL_TILES && q4 == 0 && lane == 0;
         if (stamp) p.tl[t * 8 + 5] = clock64();
-        mbar_wait_relaxed(&t_full[b], (uint32_t)((t / TBUF) & 1));
+        mbar_wait_relaxed(&t_full[b], (uint32_t)((t / TBUF) & 1), 256);
         if (stamp) p.tl[t * 8 + 6] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)b * TN;

@@ -528,7 +528,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
           const Item it = get_item(p, w, h);
           if (!it.valid) break;
           for (int kc = 0; kc < it.nk; ++kc) {
-            mbar_wait_relaxed(&empty[stage], phase ^ 1);     // the TMA thread sleeps until a stage is free
+            mbar_wait_relaxed(&empty[stage], phase ^ 1, 64);   // the TMA thread sleeps until a stage is free (4 stages x ~0.4 us of MMAs ahead)
             unsigned char* sb = base + stage * STAGE_BYTES;
             const int kk = it.k0 + kc * bk;
             mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -597,7 +597,7 @@ predict_tc_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constan
         if (!it.valid) break;
         // undo the exact power-of-two operand scaling of the fp16 path
         const float scl = p.f16 ? ldexpf(1.f, -(kx_exp(p.amp2[it.s]) + p.bexp[it.s])) : 1.f;
-        mbar_wait_relaxed(&tfull[buf], bphase);              // epilogue warps sleep through the item's MMAs (tens of us)
+        mbar_wait_relaxed(&tfull[buf], bphase, 1000);        // epilogue warps sleep through the item's MMAs (tens of us)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
 #pragma unroll 1

@@ -97,20 +97,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// Same wait for threads that expect to wait LONG (a producer on a free stage, an epilogue warp on its next accumulator): the
-// try_wait carries a suspend-time hint, so the thread sleeps in hardware instead of spinning through the issue slots (and the
-// power budget) of the warps that are doing the work.  ncu of the generator: SYNCS + YIELD + BRA of the spin loops were ~20 %
-// of all executed instructions.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "WAIT_LOOP_R:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-      "@P1 bra DONE_R;\n\t"
-      "bra WAIT_LOOP_R;\n\t"
-      "DONE_R:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(20000u)
-      : "memory");
+// Same wait for threads that expect to wait LONG (a producer on a free stage, an epilogue warp on its next accumulator):
+// poll, then SLEEP for `ns` before the next poll, so the waiting warp stays out of the issue slots (and the power budget) of
+// the warps that are doing the work.  ncu of the generator (r02): with a bare try_wait loop SYNCS + YIELD + BRA were ~20 % of
+// all executed instructions; with try_wait's suspend-time hint the compiler's loop (SYNCS, NANOSLEEP, BRA) still ran 4.8e8
+// iterations per launch = 29 % of the executed instructions -- the hint does not keep the thread asleep.  An explicit sleep
+// of a few hundred nanoseconds costs at most that much latency per tile and removes the polling.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 256) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -257,6 +257,8 @@ class GPEIEngine(object):
         # both large and badly conditioned.
         self.guard_threshold = float(os.environ.get("SMK_TC_GUARD", "0"))
         self.last = {}
+        self._deferred_info = []
+        self._chunk_cache = {}
         self.last_guard = None
         self.timers = None   # set to {} to record (start, end) CUDA events per stage on the launch stream
         self._pool = {}      # (stream, shape, dtype) -> free tensors: the big per-call buffers are recycled, never re-allocated
@@ -355,6 +357,18 @@ class GPEIEngine(object):
         on the tensor-core path -- the explicit inverse (tf32 pair, fp16 pair, the transposed pair of the inversion
         workspace: 20 B per element of Np^2) and the cross-covariance chunk (4 B per (candidate, observation) and
         sample, capped by the library's 20 GB chunk budget)."""
+        # cudaMemGetInfo is a driver call that can take milliseconds next to a busy GPU (and it is on the path of every
+        # sweep): asked again only when the allocator's own counter moved by more than 1 GB since the last answer
+        alloc = torch.cuda.memory_allocated(self.device)
+        key = (Npad, ldm, F)
+        hit = self._chunk_cache.get(key)
+        if hit is not None and abs(alloc - hit[0]) < (1 << 30):
+            return hit[1]
+        ans = self._max_samples_per_chunk(Npad, ldm, F)
+        self._chunk_cache[key] = (alloc, ans)
+        return ans
+
+    def _max_samples_per_chunk(self, Npad, ldm, F):
         free, _ = torch.cuda.mem_get_info(self.device)
         free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
         free += self.pooled_bytes()           # recycled (or dropped by take() on demand)
@@ -701,8 +715,12 @@ class GPEIEngine(object):
 
     # ------------------------------------------------------------------ whole path
     def ei_over_hypers_device(self, kind, hyper_samples, comp, pend, cand, vals, normals=None,
-                              time_hyper_samples=None, durs_log=None, want_matrix=True, inputs_on_device=None):
+                              time_hyper_samples=None, durs_log=None, want_matrix=True, inputs_on_device=None,
+                              defer_pd_check=False):
         """Runs the batched path; returns (ei [S][ldm] or None, ei_sum [ldm], M) as device tensors.
+
+        ``defer_pd_check``: do not read the factorisations' status words back here (one host synchronisation per chunk);
+        the caller calls check_deferred() before it uses the results -- back-to-back calls then queue without draining the GPU.
 
         ``normals`` (P,F): the fantasy standard normals the reference draws on the host (OPT:588-589).
         ``time_hyper_samples`` + ``durs_log``: EI per second (PSEC:437-548).
@@ -729,12 +747,24 @@ class GPEIEngine(object):
                                 None if time_hyper_samples is None else time_hyper_samples[s0:s0 + chunk],
                                 durs_log, resident=r, cand_dev=Cd)
             ei, _ = self.ei_prepared(prep, Cd, want_matrix, ei_sum, cand_host=cand)
-            prep.fac.check_pd()     # one host sync per chunk, after everything is queued
+            if defer_pd_check:
+                self._deferred_info.append(prep.fac.info)
+            else:
+                prep.fac.check_pd()     # one host sync per chunk, after everything is queued
             if want_matrix:
                 ei_all[s0:s0 + prep.S] = ei
             del prep
         self.last = dict(N=N, M=M, S=S, P=P, chunk=chunk)
         return ei_all, ei_sum, M
+
+    def check_deferred(self):
+        """Raises numpy.linalg.LinAlgError (like spla.cholesky) if any factorisation queued with defer_pd_check failed."""
+        infos, self._deferred_info = self._deferred_info, []
+        for info in infos:
+            bad = np.nonzero(info.cpu().numpy())[0]
+            if bad.size:
+                raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite (hyper-sample %d)"
+                                            % (int(info[int(bad[0])]), int(bad[0])))
 
     def can_overlap(self, N, S, P, time_hyper_samples):
         return (self.overlap and S >= 4 and P == 0 and time_hyper_samples is None and self.chain_for(N) == "tc")
