@@ -482,7 +482,9 @@ bool kxt_tc_supported(int D, int S) {
 // samples most of the 128 TMEM lanes (= epilogue threads) idle: S = 5 uses 15 lanes and the SIMT generator is 3x faster there
 // (22 vs 6.6 ms per step of the 8-GPU per-rank shape); from half the lanes on the tensor-core generator wins.
 bool kxt_tc_preferred(int D, int S) {
-  return kxt_tc_supported(D, S) && ktc::slots(S, ktc::MAXD) * S >= 64;
+  static int min_lanes = -1;
+  if (min_lanes < 0) { const char* e = getenv("SMK_KXT_TC_MIN_LANES"); min_lanes = e ? atoi(e) : 64; }
+  return kxt_tc_supported(D, S) && ktc::slots(S, ktc::MAXD) * S >= min_lanes;
 }
 
 int kxt_tc_ngroups(int) { return ktc::NGRP; }       // mean partial planes per chunk
