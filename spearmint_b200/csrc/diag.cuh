@@ -381,17 +381,8 @@ __device__ void diag_factor_block(T* __restrict__ Ab, int ld, T* __restrict__ wd
     __syncthreads();
     DIAG_STAMP(4 + 4 * p);
     // ... then the next piece's factorisation (warp 0) next to the rest of the update and the stores of column p
-#ifndef SMK_DIAG_LA
-#define SMK_DIAG_LA 3
-#endif
-    if (!(SMK_DIAG_LA & 1)) { diag_update<NB>(a, p, 1); __syncthreads(); }
-    if (!(SMK_DIAG_LA & 2)) { if (warp) store_column(p); __syncthreads(); }
-    DIAG_STAMP(4 + 4 * p);
     if (warp == 0) { chol_piece(p + 1); DIAG_STAMP(5 + 4 * p); }
-    else {
-      if (SMK_DIAG_LA & 1) diag_update<NB>(a, p, 1);
-      if (SMK_DIAG_LA & 2) store_column(p);
-    }
+    else { diag_update<NB>(a, p, 1); store_column(p); }
     __syncthreads();
     DIAG_STAMP(6 + 4 * p);
   }
