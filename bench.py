@@ -263,6 +263,17 @@ def run_b200_arm(args, D, N, M, S):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+        # The all-cores thread setting at the top of this file is for the CPU arm (rank 0 alone).  Here every rank runs host
+        # code of its own (dtype conversions of the uploads are OpenMP loops in torch): N ranks x all cores oversubscribes the
+        # host N times and the spinning OpenMP teams cost the plugin call ~13 ms per extra rank (e2e 139 ms at 8 GPUs against
+        # 34 ms of device time).  Each rank gets its share of the cores.
+        share = max(1, _CORES // world)
+        torch.set_num_threads(share)
+        try:
+            import threadpoolctl
+            threadpoolctl.threadpool_limits(limits=share)
+        except Exception:
+            pass
     backend = DeviceBackend(device="cuda:%d" % local)
     eng = backend.eng32
     comp, cand, vals, hs = synth(D, N, M, S)
