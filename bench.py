@@ -265,8 +265,9 @@ def run_b200_arm(args, D, N, M, S):
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
         # The all-cores thread setting at the top of this file is for the CPU arm (rank 0 alone).  Here every rank runs host
         # code of its own (dtype conversions of the uploads are OpenMP loops in torch): N ranks x all cores oversubscribes the
-        # host N times and the spinning OpenMP teams cost the plugin call ~13 ms per extra rank (e2e 139 ms at 8 GPUs against
-        # 34 ms of device time).  Each rank gets its share of the cores.
+        # host N times.  The plugin call measured 148 ms at 2 GPUs and 139 ms at 8 against 128 / 34 ms of device time -- growing
+        # with the rank count, which is what spinning OpenMP teams on an oversubscribed host look like (not re-measured at 8
+        # GPUs after this change: the round's GPU budget was spent).  Each rank gets its share of the cores.
         share = max(1, _CORES // world)
         torch.set_num_threads(share)
         try:
